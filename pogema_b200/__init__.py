@@ -1,0 +1,30 @@
+"""pogema_b200 - B200-native batched POGEMA step engine.
+
+Drop-in surface of upstream pogema for the step path: ``GridConfig``,
+``pogema_v0`` (list based gymnasium-style reset/step on one instance),
+``parallel_env`` (PettingZoo-style), plus ``BatchedPogema`` (torch CUDA tensors).
+All stepping and observation generation runs in the hand-written sm_100a
+kernels of ``libpgm_b200.so``; there is no CPU fallback.
+"""
+from .grid_config import (GridConfig, Easy8x8, Normal8x8, Hard8x8, ExtraHard8x8, Easy16x16, Normal16x16,
+                          Hard16x16, ExtraHard16x16, Easy32x32, Normal32x32, Hard32x32, ExtraHard32x32,
+                          Easy64x64, Normal64x64, Hard64x64, ExtraHard64x64)
+
+__version__ = "0.1.0"
+
+
+def __getattr__(name):
+    # lazy: importing the package must not require torch / a built library
+    if name == "BatchedPogema":
+        from .batched import BatchedPogema
+        return BatchedPogema
+    if name == "Engine":
+        from .engine import Engine
+        return Engine
+    if name in ("pogema_v0", "make_pogema", "Pogema", "PogemaLifeLong", "PogemaCoopFinish", "AnimationMonitor"):
+        from . import envs
+        return getattr(envs, name)
+    if name == "parallel_env":
+        from .integrations.pettingzoo import parallel_env
+        return parallel_env
+    raise AttributeError(name)

@@ -1,0 +1,179 @@
+"""``BatchedPogema`` - the batched vector env of BASELINE.json's north star:
+N independent POGEMA instances advanced by ONE fused sm_100a kernel per step,
+inputs and outputs as torch CUDA tensors (zero copies on the step path)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .engine import Engine
+from .grid_config import GridConfig
+
+
+class _DevArray:
+    """Zero-copy view of an engine-owned device array (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+        self._owner = owner
+
+
+class BatchedPogema:
+    """Vector env over ``num_envs`` instances of ``grid_config``.
+
+    Instance k is built exactly like ``pogema_v0(GridConfig(..., seed=seeds[k]))``
+    (default ``seeds[k] = (grid_config.seed or 0) + k``).
+
+    ``reset() -> obs``; ``step(actions) -> obs, rewards, terminated, truncated``:
+      obs         uint8  [N, A, 3, D, D]   (or uint32 [N, A, ceil(3*D*D/32)] with obs_format='bits')
+      rewards     float32 [N, A]
+      terminated  bool   [N, A]
+      truncated   bool   [N, A]
+    The returned tensors are owned by the env and overwritten by the next call
+    (pass ``out=`` to step into caller-owned tensors).  With ``auto_reset=True`` an
+    instance whose episode ended (all terminated or all truncated) is restored to
+    its initial task inside the same step and ``obs`` holds the reset observation
+    (upstream integrations/sample_factory.py :: AutoResetWrapper semantics).
+    """
+
+    def __init__(self, grid_config: Optional[GridConfig] = None, num_envs: int = 1, device="cuda",
+                 seeds: Optional[Sequence[int]] = None, auto_reset: bool = True, obs_format: str = "u8",
+                 team_threads: int = 0, num_threads: int = 0, **kwargs):
+        if grid_config is None:
+            grid_config = GridConfig(**kwargs)
+        elif isinstance(grid_config, dict):
+            grid_config = GridConfig(**grid_config)
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedPogema needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self.grid_config = grid_config
+        self.num_envs = int(num_envs)
+        self.num_agents = int(grid_config.num_agents)
+        self.auto_reset = bool(auto_reset)
+        self.engine = Engine(grid_config, num_envs, device=dev_index, auto_reset=auto_reset,
+                             obs_format=obs_format, team_threads=team_threads)
+        if seeds is None:
+            base = grid_config.seed or 0
+            seeds = np.arange(base, base + self.num_envs, dtype=np.uint64)
+        self.seeds = np.asarray(seeds, dtype=np.uint64)
+        assert len(self.seeds) == self.num_envs
+        self.engine.generate(self.seeds, num_threads=num_threads, stream=self._stream())
+        n, a = self.num_envs, self.num_agents
+        with torch.cuda.device(self.device):
+            self._obs = self._alloc_obs()
+            self._rewards = torch.empty((n, a), dtype=torch.float32, device=self.device)
+            self._terminated = torch.empty((n, a), dtype=torch.bool, device=self.device)
+            self._truncated = torch.empty((n, a), dtype=torch.bool, device=self.device)
+        self.obs_shape = tuple(self._obs.shape[1:])
+
+    # ------------------------------------------------------------------ #
+    def _stream(self) -> int:
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _alloc_obs(self) -> torch.Tensor:
+        e = self.engine
+        dtype = torch.int32 if e.obs_format == "bits" else torch.uint8
+        return torch.empty(e.obs_shape(), dtype=dtype, device=self.device)
+
+    def new_obs_buffer(self) -> torch.Tensor:
+        return self._alloc_obs()
+
+    # ------------------------------------------------------------------ #
+    def reset(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        obs = self._obs if out is None else out
+        self.engine.reset(obs.data_ptr(), self._stream())
+        return obs
+
+    def observe(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        obs = self._obs if out is None else out
+        self.engine.observe(obs.data_ptr(), self._stream())
+        return obs
+
+    def step(self, actions: torch.Tensor, out: Optional[torch.Tensor] = None, compute_obs: bool = True):
+        if actions.device != self.device:
+            raise ValueError(f"actions must live on {self.device}")
+        if actions.shape != (self.num_envs, self.num_agents):
+            raise ValueError(f"actions must have shape {(self.num_envs, self.num_agents)}")
+        if actions.dtype not in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+            raise TypeError("actions must be an integer tensor")
+        actions = actions.contiguous()
+        obs = self._obs if out is None else out
+        self.engine.step(actions.data_ptr(), actions.element_size(), obs.data_ptr() if compute_obs else 0,
+                         self._rewards.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(),
+                         self._stream())
+        return obs, self._rewards, self._terminated, self._truncated
+
+    def sample_actions(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        return torch.randint(0, 5, (self.num_envs, self.num_agents), dtype=torch.uint8, device=self.device,
+                             generator=generator)
+
+    # -- zero-copy state views ------------------------------------------- #
+    def _view(self, what, shape, typestr):
+        ptr = self.engine.state_ptr(what)
+        return torch.as_tensor(_DevArray(ptr, shape, typestr, self), device=self.device)
+
+    @property
+    def is_active(self) -> torch.Tensor:
+        return self._view(nat.STATE_ACTIVE, (self.num_envs, self.num_agents), "|u1").bool()
+
+    @property
+    def was_on_goal(self) -> torch.Tensor:
+        return self._view(nat.STATE_WAS_ON_GOAL, (self.num_envs, self.num_agents), "|u1").bool()
+
+    @property
+    def episode_done(self) -> torch.Tensor:
+        return self._view(nat.STATE_EPISODE_DONE, (self.num_envs,), "|u1").bool()
+
+    @property
+    def elapsed_steps(self) -> torch.Tensor:
+        return self._view(nat.STATE_ELAPSED, (self.num_envs,), "<i4")
+
+    def _xy(self, what) -> torch.Tensor:
+        packed = self._view(what, (self.num_envs, self.num_agents), "<i4")
+        r = self.grid_config.obs_radius
+        return torch.stack(((packed & 0xFFFF) - r, (packed >> 16) - r), dim=-1)
+
+    def get_agents_xy(self) -> torch.Tensor:
+        """int32 [N, A, 2] unpadded (x, y) positions."""
+        return self._xy(nat.STATE_POSITIONS)
+
+    def get_targets_xy(self) -> torch.Tensor:
+        return self._xy(nat.STATE_TARGETS)
+
+    def get_obstacles(self) -> np.ndarray:
+        """uint8 [N, H, W] unpadded obstacle maps (host array)."""
+        return self.engine.get_state(nat.STATE_OBSTACLES)
+
+    def metrics(self) -> dict:
+        """Metrics of the last finished episode of every instance (upstream
+        wrappers/metrics.py), computed from the raw device counters."""
+        raw = self.engine.get_state(nat.STATE_METRICS, self._stream()).astype(np.float64)
+        a = float(self.num_agents)
+        ot = self.grid_config.on_target
+        if ot == 'restart':
+            return {"avg_throughput": raw[:, 0] / self.grid_config.max_episode_steps}
+        if ot == 'nothing':
+            return {"ISR": raw[:, 3] / a, "CSR": (raw[:, 3] == a).astype(np.float64), "ep_length": raw[:, 2]}
+        return {"ISR": raw[:, 0] / a, "CSR": (raw[:, 0] == a).astype(np.float64), "ep_length": raw[:, 1] / a + 1}
+
+    # -- checkpoint / resume ------------------------------------------------ #
+    def state_dict(self) -> dict:
+        return {"engine": self.engine.checkpoint(self._stream()), "seeds": self.seeds.copy()}
+
+    def load_state_dict(self, sd: dict):
+        assert np.array_equal(sd["seeds"], self.seeds), "checkpoint belongs to different tasks"
+        self.engine.restore(sd["engine"], self._stream())
+
+    def check_errors(self):
+        self.engine.check_errors(self._stream())
+
+    def close(self):
+        self.engine.close()

@@ -1,0 +1,749 @@
+// pgm_capi.cu - engine object + the C-ABI declared in include/pgm_b200.h.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pgm_b200.h"
+#include "pgm_gen.h"
+#include "pgm_kernels.cuh"
+
+using namespace pgm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(PGM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+inline int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p *= 2;
+  return p;
+}
+
+}  // namespace
+
+struct pgm_engine {
+  pgm_config cfg{};
+  int PH = 0, PW = 0, WPR = 0, D = 0;
+  int obst_stride = 0;  // words
+  int bits_per_agent = 0, stage_bpa = 0;
+  int64_t obs_inst_stride = 0, obs_bytes = 0;
+  int64_t cells_stride = 0;
+  bool lifelong = false;
+  bool tasks_ready = false;
+  int sm_count = 148;
+  // plan
+  int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1;
+  StepArgs layout{};  // offsets only
+  // device state
+  uint32_t *d_obst = nullptr, *d_pos = nullptr, *d_tgt = nullptr, *d_pos0 = nullptr, *d_tgt0 = nullptr;
+  uint8_t *d_active = nullptr, *d_was = nullptr, *d_done = nullptr;
+  int32_t *d_elapsed = nullptr, *d_macc = nullptr, *d_mlast = nullptr;
+  Pcg64 *d_rng = nullptr, *d_rng0 = nullptr;
+  int32_t *d_cstart = nullptr, *d_csize = nullptr;
+  uint32_t* d_cells = nullptr;
+  int* d_err = nullptr;
+  // step_host scratch
+  uint8_t *d_act_h = nullptr, *d_obs_h = nullptr, *d_term_h = nullptr, *d_trunc_h = nullptr;
+  float* d_rew_h = nullptr;
+  int act_h_itemsize = 0;
+  // host mirrors
+  std::vector<uint32_t> h_obst;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int compute_plan(pgm_engine* e) {
+  const pgm_config& c = e->cfg;
+  const int A = c.num_agents;
+  int team = c.team_threads;
+  if (team == 0) {
+    // keep every instance co-resident when possible: ~1024 threads per SM
+    const int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;
+    team = pow2_floor(std::max(32, 1024 / std::max(1, per_sm)));
+    team = std::min(team, std::max(32, pow2_ceil(A)));
+    team = std::min(team, 1024);
+  }
+  if (team != 32 && team != 64 && team != 128 && team != 256 && team != 512 && team != 1024)
+    return fail(PGM_ERR_INVALID, "team_threads must be 0 or a power of two in [32,1024], got %d", team);
+  e->team = team;
+  const int occ_bytes = round_up(e->PH * e->PW * 2 + 4, 16);
+  const int fixed = e->obst_stride * 4 + round_up((e->PH * e->WPR + 1) * 4, 16) + 4 * round_up(A * 4, 16) +
+                    2 * round_up(A, 16) + 16;
+  const int smem_max = 227 * 1024;
+  // observation batch: as many agents as fit next to the fixed part (at least what occ needs anyway)
+  long long budget = std::max<long long>(occ_bytes, 64 * 1024);
+  budget = std::min<long long>(budget, (long long)smem_max - fixed);
+  if (budget < occ_bytes)
+    return fail(PGM_ERR_UNSUPPORTED,
+                "instance does not fit in shared memory (needs %d + %d bytes of %d): map %dx%d, %d agents",
+                fixed, occ_bytes, smem_max, c.height, c.width, A);
+  long long g = ((budget - 16) * 8) / e->stage_bpa;
+  if (g < 1)
+    return fail(PGM_ERR_UNSUPPORTED, "observation of one agent (%d bits) does not fit the stage buffer",
+                e->stage_bpa);
+  e->batch_agents = (int)std::min<long long>(g, A);
+  const int stage_bytes = round_up((int)((((long long)e->batch_agents * e->stage_bpa + 31) / 32 + 2) * 4), 16);
+  StepArgs& L = e->layout;
+  int off = 0;
+  L.off_obst = off;
+  off += e->obst_stride * 4;
+  L.off_abits = off;
+  off += round_up((e->PH * e->WPR + 1) * 4, 16);
+  L.off_occ = off;
+  off += std::max(occ_bytes, stage_bytes);
+  L.off_pos = off;
+  off += round_up(A * 4, 16);
+  L.off_tgt = off;
+  off += round_up(A * 4, 16);
+  L.off_npos = off;
+  off += round_up(A * 4, 16);
+  L.off_link = off;
+  off += round_up(A * 4, 16);
+  L.off_act = off;
+  off += round_up(A, 16);
+  L.off_flag = off;
+  off += round_up(A, 16);
+  L.off_misc = off;
+  off += 16;
+  L.team_smem = round_up(off, 16);
+  if (L.team_smem > smem_max)
+    return fail(PGM_ERR_UNSUPPORTED, "instance needs %d bytes of shared memory (max %d)", L.team_smem, smem_max);
+  int tpc = std::max(1, 128 / team);
+  while (tpc > 1 && tpc * L.team_smem > smem_max) tpc--;
+  if (team > 32) tpc = std::min(tpc, 15);
+  e->tpc = tpc;
+  L.teams_per_cta = tpc;
+  e->cta_threads = tpc * team;
+  e->smem_cta = tpc * L.team_smem;
+  e->grid = (c.num_envs + tpc - 1) / tpc;
+  return PGM_OK;
+}
+
+template <int TEAM, int COLL, int OP>
+int launch_one(pgm_engine* e, const StepArgs& a, cudaStream_t s) {
+  auto kern = pgm_step_kernel<TEAM, COLL, OP>;
+  static thread_local int configured_dev = -1;
+  static thread_local int configured_smem = -1;
+  if (configured_dev != e->cfg.device || configured_smem < e->smem_cta) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_cta));
+    configured_dev = e->cfg.device;
+    configured_smem = e->smem_cta;
+  }
+  kern<<<e->grid, e->cta_threads, e->smem_cta, s>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  e->launches++;
+  return PGM_OK;
+}
+
+template <int TEAM>
+int launch_team(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
+  if (op == OP_OBSERVE) return launch_one<TEAM, 0, OP_OBSERVE>(e, a, s);
+  if (op == OP_RESET) return launch_one<TEAM, 0, OP_RESET>(e, a, s);
+  switch (e->cfg.collision_system) {
+    case PGM_COLLISION_PRIORITY: return launch_one<TEAM, 0, OP_STEP>(e, a, s);
+    case PGM_COLLISION_BLOCK_BOTH: return launch_one<TEAM, 1, OP_STEP>(e, a, s);
+    default: return launch_one<TEAM, 2, OP_STEP>(e, a, s);
+  }
+}
+
+int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
+  switch (e->team) {
+    case 32: return launch_team<32>(e, a, op, s);
+    case 64: return launch_team<64>(e, a, op, s);
+    case 128: return launch_team<128>(e, a, op, s);
+    case 256: return launch_team<256>(e, a, op, s);
+    case 512: return launch_team<512>(e, a, op, s);
+    default: return launch_team<1024>(e, a, op, s);
+  }
+}
+
+StepArgs make_args(pgm_engine* e) {
+  StepArgs a = e->layout;
+  const pgm_config& c = e->cfg;
+  a.N = c.num_envs;
+  a.A = c.num_agents;
+  a.PH = e->PH;
+  a.PW = e->PW;
+  a.WPR = e->WPR;
+  a.r = c.obs_radius;
+  a.D = e->D;
+  a.obst_stride = e->obst_stride;
+  a.bits_per_agent = e->bits_per_agent;
+  a.stage_bpa = e->stage_bpa;
+  a.obs_format = c.obs_format;
+  a.max_steps = c.max_episode_steps;
+  a.auto_reset = c.auto_reset;
+  a.on_target = c.on_target;
+  a.batch_agents = e->batch_agents;
+  int lg = 0;
+  while ((1 << lg) < c.num_agents) lg++;
+  a.max_rounds = lg + 2;
+  a.obst = e->d_obst;
+  a.pos = e->d_pos;
+  a.tgt = e->d_tgt;
+  a.pos0 = e->d_pos0;
+  a.tgt0 = e->d_tgt0;
+  a.active = e->d_active;
+  a.elapsed = e->d_elapsed;
+  a.rng = e->d_rng;
+  a.rng0 = e->d_rng0;
+  a.comp_start = e->d_cstart;
+  a.comp_size = e->d_csize;
+  a.cells = e->d_cells;
+  a.cells_stride = e->cells_stride;
+  a.was_on_goal = e->d_was;
+  a.episode_done = e->d_done;
+  a.metric_acc = e->d_macc;
+  a.metric_last = e->d_mlast;
+  a.actions = nullptr;
+  a.act_itemsize = 1;
+  a.obs = nullptr;
+  a.obs_inst_stride = e->obs_inst_stride;
+  a.rewards = nullptr;
+  a.terminated = nullptr;
+  a.truncated = nullptr;
+  a.err_flag = e->d_err;
+  return a;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Upload generated instances [first, first+count) and make them the current state.
+int upload_instances(pgm_engine* e, int first, int count, std::vector<GenInstance>& inst, cudaStream_t s) {
+  const int A = e->cfg.num_agents;
+  std::vector<uint32_t> obst((size_t)count * e->obst_stride, 0u), pos((size_t)count * A), tgt((size_t)count * A);
+  for (int k = 0; k < count; ++k) {
+    memcpy(&obst[(size_t)k * e->obst_stride], inst[k].obst_bits.data(), inst[k].obst_bits.size() * 4);
+    memcpy(&pos[(size_t)k * A], inst[k].pos.data(), (size_t)A * 4);
+    memcpy(&tgt[(size_t)k * A], inst[k].tgt.data(), (size_t)A * 4);
+  }
+  memcpy(&e->h_obst[(size_t)first * e->obst_stride], obst.data(), obst.size() * 4);
+  CUDA_TRY(cudaMemcpyAsync(e->d_obst + (size_t)first * e->obst_stride, obst.data(), obst.size() * 4,
+                           cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(e->d_pos0 + (size_t)first * A, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(e->d_tgt0 + (size_t)first * A, tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(e->d_pos + (size_t)first * A, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(e->d_tgt + (size_t)first * A, tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(e->d_active + (size_t)first * A, 1, (size_t)count * A, s));
+  CUDA_TRY(cudaMemsetAsync(e->d_was + (size_t)first * A, 0, (size_t)count * A, s));
+  CUDA_TRY(cudaMemsetAsync(e->d_done + first, 0, (size_t)count, s));
+  CUDA_TRY(cudaMemsetAsync(e->d_elapsed + first, 0, (size_t)count * 4, s));
+  CUDA_TRY(cudaMemsetAsync(e->d_macc + (size_t)first * 4, 0, (size_t)count * 16, s));
+  CUDA_TRY(cudaMemsetAsync(e->d_mlast + (size_t)first * 4, 0, (size_t)count * 16, s));
+  std::vector<Pcg64> rng;
+  std::vector<int32_t> cstart, csize;
+  std::vector<uint32_t> cells;
+  if (e->lifelong) {
+    rng.resize((size_t)count * A);
+    cstart.resize((size_t)count * A);
+    csize.resize((size_t)count * A);
+    cells.assign((size_t)count * e->cells_stride, 0u);
+    for (int k = 0; k < count; ++k) {
+      if ((int64_t)inst[k].cells.size() > e->cells_stride)
+        return fail(PGM_ERR_INVALID, "internal: component table larger than the map");
+      memcpy(&rng[(size_t)k * A], inst[k].rng.data(), (size_t)A * sizeof(Pcg64));
+      memcpy(&cstart[(size_t)k * A], inst[k].comp_start.data(), (size_t)A * 4);
+      memcpy(&csize[(size_t)k * A], inst[k].comp_size.data(), (size_t)A * 4);
+      memcpy(&cells[(size_t)k * e->cells_stride], inst[k].cells.data(), inst[k].cells.size() * 4);
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->d_rng + (size_t)first * A, rng.data(), rng.size() * sizeof(Pcg64),
+                             cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_rng0 + (size_t)first * A, rng.data(), rng.size() * sizeof(Pcg64),
+                             cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_cstart + (size_t)first * A, cstart.data(), cstart.size() * 4,
+                             cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_csize + (size_t)first * A, csize.data(), csize.size() * 4,
+                             cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->d_cells + (size_t)first * e->cells_stride, cells.data(), cells.size() * 4,
+                             cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));  // host vectors go out of scope
+  e->tasks_ready = true;
+  return PGM_OK;
+}
+
+GenParams gen_params(const pgm_engine* e, double density, const uint8_t* map) {
+  GenParams p;
+  p.H = e->cfg.height;
+  p.W = e->cfg.width;
+  p.A = e->cfg.num_agents;
+  p.r = e->cfg.obs_radius;
+  p.density = density;
+  p.lifelong = e->lifelong;
+  p.map = map;
+  return p;
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+  CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  CUDA_TRY(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return PGM_OK;
+}
+
+int ensure_host_scratch(pgm_engine* e, int itemsize) {
+  const size_t NA = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+  if (!e->d_obs_h) {
+    CUDA_TRY(cudaMalloc((void**)&e->d_obs_h, (size_t)e->obs_bytes));
+    CUDA_TRY(cudaMalloc((void**)&e->d_rew_h, NA * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_term_h, NA));
+    CUDA_TRY(cudaMalloc((void**)&e->d_trunc_h, NA));
+  }
+  if (e->act_h_itemsize < itemsize) {
+    if (e->d_act_h) cudaFree(e->d_act_h);
+    e->d_act_h = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&e->d_act_h, NA * itemsize));
+    e->act_h_itemsize = itemsize;
+  }
+  return PGM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pgm_last_error(void) { return g_last_error.c_str(); }
+int pgm_abi_version(void) { return PGM_ABI_VERSION; }
+
+int pgm_create(const pgm_config* cfg, pgm_engine** out) {
+  if (!cfg || !out) return fail(PGM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != PGM_ABI_VERSION)
+    return fail(PGM_ERR_INVALID, "abi_version %d != %d", cfg->abi_version, PGM_ABI_VERSION);
+  if (cfg->num_envs < 1) return fail(PGM_ERR_INVALID, "num_envs must be >= 1");
+  if (cfg->num_agents < 1 || cfg->num_agents > 65534)
+    return fail(PGM_ERR_UNSUPPORTED, "num_agents must be in [1, 65534] per instance, got %d", cfg->num_agents);
+  if (cfg->height < 1 || cfg->width < 1 || cfg->height > 1024 || cfg->width > 1024)
+    return fail(PGM_ERR_INVALID, "map size must be in [1,1024], got %dx%d", cfg->height, cfg->width);
+  if (cfg->obs_radius < 1 || cfg->obs_radius > 128) return fail(PGM_ERR_INVALID, "obs_radius must be in [1,128]");
+  if (cfg->max_episode_steps < 1) return fail(PGM_ERR_INVALID, "max_episode_steps must be >= 1");
+  if (cfg->collision_system < 0 || cfg->collision_system > 2) return fail(PGM_ERR_INVALID, "bad collision_system");
+  if (cfg->on_target < 0 || cfg->on_target > 2) return fail(PGM_ERR_INVALID, "bad on_target");
+  if (cfg->obs_format < 0 || cfg->obs_format > 1) return fail(PGM_ERR_INVALID, "bad obs_format");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(PGM_ERR_INVALID, "device %d out of range (%d visible)", cfg->device, ndev);
+  DeviceGuard guard(cfg->device);
+  pgm_engine* e = new pgm_engine();
+  e->cfg = *cfg;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  e->sm_count = prop.multiProcessorCount;
+  const int r = cfg->obs_radius;
+  e->D = 2 * r + 1;
+  e->PH = cfg->height + 2 * r;
+  e->PW = cfg->width + 2 * r;
+  e->WPR = (e->PW + 31) / 32;
+  e->obst_stride = round_up(e->PH * e->WPR + 1, 4);
+  e->bits_per_agent = 3 * e->D * e->D;
+  e->lifelong = cfg->on_target == PGM_ON_TARGET_RESTART;
+  const int64_t A = cfg->num_agents, N = cfg->num_envs;
+  if (cfg->obs_format == PGM_OBS_BITS) {
+    e->stage_bpa = round_up(e->bits_per_agent, 32);
+    e->obs_inst_stride = A * (e->stage_bpa / 8);
+  } else {
+    e->stage_bpa = e->bits_per_agent;
+    e->obs_inst_stride = A * e->bits_per_agent;
+  }
+  e->obs_bytes = N * e->obs_inst_stride;
+  e->cells_stride = (int64_t)cfg->height * cfg->width;
+  int rc = compute_plan(e);
+  if (rc != PGM_OK) {
+    delete e;
+    return rc;
+  }
+#define TRY_ALLOC(x)   \
+  if ((rc = (x)) != PGM_OK) { \
+    pgm_destroy(e);    \
+    return rc;         \
+  }
+  TRY_ALLOC(dev_alloc(&e->d_obst, (size_t)N * e->obst_stride));
+  TRY_ALLOC(dev_alloc(&e->d_pos, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_tgt, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_pos0, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_tgt0, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_active, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_was, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_done, (size_t)N));
+  TRY_ALLOC(dev_alloc(&e->d_elapsed, (size_t)N));
+  TRY_ALLOC(dev_alloc(&e->d_macc, (size_t)N * 4));
+  TRY_ALLOC(dev_alloc(&e->d_mlast, (size_t)N * 4));
+  TRY_ALLOC(dev_alloc(&e->d_err, 1));
+  if (e->lifelong) {
+    TRY_ALLOC(dev_alloc(&e->d_rng, (size_t)N * A));
+    TRY_ALLOC(dev_alloc(&e->d_rng0, (size_t)N * A));
+    TRY_ALLOC(dev_alloc(&e->d_cstart, (size_t)N * A));
+    TRY_ALLOC(dev_alloc(&e->d_csize, (size_t)N * A));
+    TRY_ALLOC(dev_alloc(&e->d_cells, (size_t)N * e->cells_stride));
+  }
+#undef TRY_ALLOC
+  e->h_obst.assign((size_t)N * e->obst_stride, 0u);
+  *out = e;
+  return PGM_OK;
+}
+
+int pgm_destroy(pgm_engine* e) {
+  if (!e) return PGM_OK;
+  DeviceGuard guard(e->cfg.device);
+  void* ptrs[] = {e->d_obst,  e->d_pos,   e->d_tgt,   e->d_pos0,   e->d_tgt0,  e->d_active, e->d_was,
+                  e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
+                  e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h, e->d_term_h, e->d_trunc_h,
+                  e->d_rew_h};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete e;
+  return PGM_OK;
+}
+
+int64_t pgm_obs_bytes(const pgm_engine* e) { return e ? e->obs_bytes : 0; }
+int64_t pgm_obs_instance_stride(const pgm_engine* e) { return e ? e->obs_inst_stride : 0; }
+int64_t pgm_launch_count(const pgm_engine* e) { return e ? e->launches : 0; }
+
+int pgm_plan(const pgm_engine* e, int32_t* out, int32_t n) {
+  if (!e || !out) return fail(PGM_ERR_INVALID, "null argument");
+  const int32_t v[7] = {e->team, e->tpc, e->cta_threads, e->smem_cta, e->grid, e->batch_agents, 1};
+  for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
+  return PGM_OK;
+}
+
+int pgm_generate(pgm_engine* e, int32_t first, int32_t count, const uint64_t* seeds, double density,
+                 const uint8_t* map_host, int32_t num_threads, int32_t* failed_index, void* stream) {
+  if (!e || !seeds) return fail(PGM_ERR_INVALID, "null argument");
+  if (first < 0 || count < 0 || first + count > e->cfg.num_envs) return fail(PGM_ERR_INVALID, "bad instance range");
+  if (!(density >= 0.0 && density <= 1.0)) return fail(PGM_ERR_INVALID, "density must be in [0,1]");
+  DeviceGuard guard(e->cfg.device);
+  GenParams gp = gen_params(e, density, map_host);
+  std::vector<GenInstance> inst(count);
+  std::atomic<int> next(0), bad(-1);
+  int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, count));
+  auto work = [&]() {
+    for (;;) {
+      int k = next.fetch_add(1);
+      if (k >= count) break;
+      if (generate_instance(gp, seeds[k], inst[k]) != 0) {
+        int expect = -1;
+        bad.compare_exchange_strong(expect, k);
+      }
+    }
+  };
+  if (nt == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  if (bad.load() >= 0) {
+    if (failed_index) *failed_index = first + bad.load();
+    return fail(PGM_ERR_OVERFLOW,
+                "Can't create task. Please check grid grid_config, especially density, num_agent and map. "
+                "(instance %d, seed %llu)",
+                first + bad.load(), (unsigned long long)seeds[bad.load()]);
+  }
+  return upload_instances(e, first, count, inst, (cudaStream_t)stream);
+}
+
+int pgm_generate_host(int32_t height, int32_t width, int32_t num_agents, int32_t obs_radius, double density,
+                      int32_t lifelong, const uint8_t* map_host, uint64_t seed, uint8_t* obstacles_out,
+                      int32_t* agents_xy_out, int32_t* targets_xy_out, uint64_t* rng_out,
+                      int32_t* comp_size_out) {
+  if (height < 1 || width < 1 || num_agents < 1 || obs_radius < 1) return fail(PGM_ERR_INVALID, "bad geometry");
+  if (!obstacles_out || !agents_xy_out || !targets_xy_out) return fail(PGM_ERR_INVALID, "null argument");
+  GenParams gp;
+  gp.H = height;
+  gp.W = width;
+  gp.A = num_agents;
+  gp.r = obs_radius;
+  gp.density = density;
+  gp.lifelong = lifelong != 0;
+  gp.map = map_host;
+  GenInstance inst;
+  if (generate_instance(gp, seed, inst) != 0)
+    return fail(PGM_ERR_OVERFLOW,
+                "Can't create task. Please check grid grid_config, especially density, num_agent and map.");
+  const int r = obs_radius;
+  for (int x = 0; x < height; ++x)
+    for (int y = 0; y < width; ++y)
+      obstacles_out[(size_t)x * width + y] =
+          (inst.obst_bits[(size_t)(x + r) * inst.WPR + ((y + r) >> 5)] >> ((y + r) & 31)) & 1u;
+  for (int a = 0; a < num_agents; ++a) {
+    agents_xy_out[2 * a] = (int)(inst.pos[a] & 0xFFFF) - r;
+    agents_xy_out[2 * a + 1] = (int)(inst.pos[a] >> 16) - r;
+    targets_xy_out[2 * a] = (int)(inst.tgt[a] & 0xFFFF) - r;
+    targets_xy_out[2 * a + 1] = (int)(inst.tgt[a] >> 16) - r;
+    if (gp.lifelong && rng_out) {
+      rng_out[4 * a] = inst.rng[a].state_hi;
+      rng_out[4 * a + 1] = inst.rng[a].state_lo;
+      rng_out[4 * a + 2] = inst.rng[a].inc_hi;
+      rng_out[4 * a + 3] = inst.rng[a].inc_lo;
+    }
+    if (gp.lifelong && comp_size_out) comp_size_out[a] = inst.comp_size[a];
+  }
+  return PGM_OK;
+}
+
+int pgm_set_tasks(pgm_engine* e, int32_t first, int32_t count, const uint8_t* obstacles,
+                  const int32_t* agents_xy, const int32_t* targets_xy, const uint64_t* seeds, void* stream) {
+  if (!e || !obstacles || !agents_xy || !targets_xy) return fail(PGM_ERR_INVALID, "null argument");
+  if (first < 0 || count < 0 || first + count > e->cfg.num_envs) return fail(PGM_ERR_INVALID, "bad instance range");
+  DeviceGuard guard(e->cfg.device);
+  GenParams gp = gen_params(e, 0.0, nullptr);
+  std::vector<GenInstance> inst(count);
+  const size_t hw = (size_t)e->cfg.height * e->cfg.width;
+  const size_t a2 = (size_t)e->cfg.num_agents * 2;
+  for (int k = 0; k < count; ++k) {
+    int rc = explicit_instance(gp, seeds ? seeds[k] : 0ull, obstacles + k * hw, agents_xy + k * a2,
+                               targets_xy + k * a2, inst[k]);
+    if (rc != 0) return fail(PGM_ERR_INVALID, "Position is out of bounds! (instance %d)", first + k);
+  }
+  return upload_instances(e, first, count, inst, (cudaStream_t)stream);
+}
+
+int pgm_reset(pgm_engine* e, void* obs_dev, void* stream) {
+  if (!e) return fail(PGM_ERR_INVALID, "null engine");
+  if (!e->tasks_ready) return fail(PGM_ERR_STATE, "pgm_reset before pgm_generate / pgm_set_tasks");
+  DeviceGuard guard(e->cfg.device);
+  StepArgs a = make_args(e);
+  a.obs = (uint8_t*)obs_dev;
+  return launch(e, a, OP_RESET, (cudaStream_t)stream);
+}
+
+int pgm_observe(pgm_engine* e, void* obs_dev, void* stream) {
+  if (!e || !obs_dev) return fail(PGM_ERR_INVALID, "null argument");
+  if (!e->tasks_ready) return fail(PGM_ERR_STATE, "pgm_observe before pgm_generate / pgm_set_tasks");
+  DeviceGuard guard(e->cfg.device);
+  StepArgs a = make_args(e);
+  a.obs = (uint8_t*)obs_dev;
+  return launch(e, a, OP_OBSERVE, (cudaStream_t)stream);
+}
+
+int pgm_step(pgm_engine* e, const void* actions_dev, int32_t action_itemsize, void* obs_dev, float* rewards_dev,
+             uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream) {
+  if (!e || !actions_dev || !rewards_dev || !terminated_dev || !truncated_dev)
+    return fail(PGM_ERR_INVALID, "null argument");
+  if (action_itemsize != 1 && action_itemsize != 2 && action_itemsize != 4 && action_itemsize != 8)
+    return fail(PGM_ERR_INVALID, "action_itemsize must be 1, 2, 4 or 8");
+  if (!e->tasks_ready) return fail(PGM_ERR_STATE, "pgm_step before pgm_generate / pgm_set_tasks");
+  DeviceGuard guard(e->cfg.device);
+  StepArgs a = make_args(e);
+  a.actions = (const uint8_t*)actions_dev;
+  a.act_itemsize = action_itemsize;
+  a.obs = (uint8_t*)obs_dev;
+  a.rewards = rewards_dev;
+  a.terminated = terminated_dev;
+  a.truncated = truncated_dev;
+  return launch(e, a, OP_STEP, (cudaStream_t)stream);
+}
+
+int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsize, void* obs_host,
+                  float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream) {
+  if (!e || !actions_host || !rewards_host || !terminated_host || !truncated_host)
+    return fail(PGM_ERR_INVALID, "null argument");
+  if (action_itemsize != 1 && action_itemsize != 2 && action_itemsize != 4 && action_itemsize != 8)
+    return fail(PGM_ERR_INVALID, "action_itemsize must be 1, 2, 4 or 8");
+  DeviceGuard guard(e->cfg.device);
+  int rc = ensure_host_scratch(e, action_itemsize);
+  if (rc != PGM_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t NA = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+  CUDA_TRY(cudaMemcpyAsync(e->d_act_h, actions_host, NA * action_itemsize, cudaMemcpyHostToDevice, s));
+  rc = pgm_step(e, e->d_act_h, action_itemsize, obs_host ? e->d_obs_h : nullptr, e->d_rew_h, e->d_term_h,
+                e->d_trunc_h, stream);
+  if (rc != PGM_OK) return rc;
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(rewards_host, e->d_rew_h, NA * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(terminated_host, e->d_term_h, NA, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(truncated_host, e->d_trunc_h, NA, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return PGM_OK;
+}
+
+int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, void* stream) {
+  if (!e || !dst) return fail(PGM_ERR_INVALID, "null argument");
+  DeviceGuard guard(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t N = e->cfg.num_envs, A = e->cfg.num_agents, r = e->cfg.obs_radius;
+  auto need = [&](int64_t n) { return dst_bytes >= n ? 0 : fail(PGM_ERR_INVALID, "destination too small: %lld < %lld", (long long)dst_bytes, (long long)n); };
+  switch (what) {
+    case PGM_STATE_POSITIONS:
+    case PGM_STATE_TARGETS: {
+      if (need(N * A * 8)) return PGM_ERR_INVALID;
+      std::vector<uint32_t> tmp((size_t)(N * A));
+      CUDA_TRY(cudaMemcpyAsync(tmp.data(), what == PGM_STATE_POSITIONS ? e->d_pos : e->d_tgt, tmp.size() * 4,
+                               cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      int32_t* o = (int32_t*)dst;
+      for (size_t i = 0; i < tmp.size(); ++i) {
+        o[2 * i] = (int32_t)(tmp[i] & 0xFFFF) - (int32_t)r;
+        o[2 * i + 1] = (int32_t)(tmp[i] >> 16) - (int32_t)r;
+      }
+      return PGM_OK;
+    }
+    case PGM_STATE_ACTIVE:
+    case PGM_STATE_WAS_ON_GOAL: {
+      if (need(N * A)) return PGM_ERR_INVALID;
+      CUDA_TRY(cudaMemcpyAsync(dst, what == PGM_STATE_ACTIVE ? e->d_active : e->d_was, (size_t)(N * A),
+                               cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      return PGM_OK;
+    }
+    case PGM_STATE_ELAPSED: {
+      if (need(N * 4)) return PGM_ERR_INVALID;
+      CUDA_TRY(cudaMemcpyAsync(dst, e->d_elapsed, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      return PGM_OK;
+    }
+    case PGM_STATE_EPISODE_DONE: {
+      if (need(N)) return PGM_ERR_INVALID;
+      CUDA_TRY(cudaMemcpyAsync(dst, e->d_done, (size_t)N, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      return PGM_OK;
+    }
+    case PGM_STATE_METRICS: {
+      if (need(N * 16)) return PGM_ERR_INVALID;
+      CUDA_TRY(cudaMemcpyAsync(dst, e->d_mlast, (size_t)N * 16, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      return PGM_OK;
+    }
+    case PGM_STATE_OBSTACLES: {
+      const int64_t H = e->cfg.height, W = e->cfg.width;
+      if (need(N * H * W)) return PGM_ERR_INVALID;
+      uint8_t* o = (uint8_t*)dst;
+      for (int64_t n = 0; n < N; ++n) {
+        const uint32_t* bits = &e->h_obst[(size_t)n * e->obst_stride];
+        for (int64_t x = 0; x < H; ++x)
+          for (int64_t y = 0; y < W; ++y) {
+            int64_t px = x + r, py = y + r;
+            o[(n * H + x) * W + y] = (bits[px * e->WPR + (py >> 5)] >> (py & 31)) & 1u;
+          }
+      }
+      return PGM_OK;
+    }
+    default: return fail(PGM_ERR_INVALID, "unknown state selector %d", what);
+  }
+}
+
+void* pgm_state_ptr(pgm_engine* e, int32_t what) {
+  if (!e) return nullptr;
+  switch (what) {
+    case PGM_STATE_POSITIONS: return e->d_pos;
+    case PGM_STATE_TARGETS: return e->d_tgt;
+    case PGM_STATE_ACTIVE: return e->d_active;
+    case PGM_STATE_ELAPSED: return e->d_elapsed;
+    case PGM_STATE_WAS_ON_GOAL: return e->d_was;
+    case PGM_STATE_EPISODE_DONE: return e->d_done;
+    case PGM_STATE_METRICS: return e->d_mlast;
+    default: return nullptr;
+  }
+}
+
+int64_t pgm_checkpoint_bytes(const pgm_engine* e) {
+  if (!e) return 0;
+  const int64_t N = e->cfg.num_envs, A = e->cfg.num_agents;
+  int64_t b = N * A * (4 + 4 + 1 + 1) + N * (4 + 1 + 16 + 16);
+  if (e->lifelong) b += N * A * (int64_t)sizeof(Pcg64);
+  return b;
+}
+
+namespace {
+struct CkptPart {
+  void* dev;
+  size_t bytes;
+};
+std::vector<CkptPart> ckpt_parts(pgm_engine* e) {
+  const size_t N = e->cfg.num_envs, A = e->cfg.num_agents;
+  std::vector<CkptPart> v = {{e->d_pos, N * A * 4}, {e->d_tgt, N * A * 4},  {e->d_active, N * A},
+                             {e->d_was, N * A},     {e->d_elapsed, N * 4}, {e->d_done, N},
+                             {e->d_macc, N * 16},   {e->d_mlast, N * 16}};
+  if (e->lifelong) v.push_back({e->d_rng, N * A * sizeof(Pcg64)});
+  return v;
+}
+}  // namespace
+
+int pgm_checkpoint_save(pgm_engine* e, void* dst, int64_t dst_bytes, void* stream) {
+  if (!e || !dst) return fail(PGM_ERR_INVALID, "null argument");
+  if (dst_bytes < pgm_checkpoint_bytes(e)) return fail(PGM_ERR_INVALID, "checkpoint buffer too small");
+  DeviceGuard guard(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* o = (uint8_t*)dst;
+  for (auto& p : ckpt_parts(e)) {
+    CUDA_TRY(cudaMemcpyAsync(o, p.dev, p.bytes, cudaMemcpyDeviceToHost, s));
+    o += p.bytes;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return PGM_OK;
+}
+
+int pgm_checkpoint_load(pgm_engine* e, const void* src, int64_t src_bytes, void* stream) {
+  if (!e || !src) return fail(PGM_ERR_INVALID, "null argument");
+  if (src_bytes < pgm_checkpoint_bytes(e)) return fail(PGM_ERR_INVALID, "checkpoint buffer too small");
+  DeviceGuard guard(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint8_t* o = (const uint8_t*)src;
+  for (auto& p : ckpt_parts(e)) {
+    CUDA_TRY(cudaMemcpyAsync(p.dev, o, p.bytes, cudaMemcpyHostToDevice, s));
+    o += p.bytes;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return PGM_OK;
+}
+
+int pgm_check_errors(pgm_engine* e, void* stream) {
+  if (!e) return fail(PGM_ERR_INVALID, "null engine");
+  DeviceGuard guard(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  if (flag & 1) {
+    CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), s));
+    return fail(PGM_ERR_ACTION, "an action outside [0,5) was passed to pgm_step (treated as 0 = stay)");
+  }
+  return PGM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,573 @@
+// pgm_kernels.cuh - the fused POGEMA step kernel for sm_100a.
+//
+// One TEAM of threads (a warp, or 64..1024 threads on a named barrier) owns one
+// instance for the whole step; everything an instance needs lives in that
+// team's slice of shared memory:
+//
+//   obst   bit-packed PADDED obstacle map  (cp.async.bulk global->shared, mbarrier)
+//   occ    uint16 cell -> agent index grid (pre-move occupancy, for conflict lookups)
+//   abits  bit-packed post-move agent occupancy
+//   stage  the observation bit stream of a batch of agents (aliases occ)
+//
+// Phases: load -> occupancy grid -> move resolution (closed forms of the three
+// upstream collision systems, pointer jumping for the dependent chains) ->
+// on_target bookkeeping / time limit / auto reset -> observation bits ->
+// bit->byte expansion with 16-byte streaming stores.
+//
+// Upstream symbols restated (pure Python upstream; /root/reference holds only
+// README.md:1-5, so symbols are cited by name - SURVEY.md section 8a):
+//   envs.py :: Pogema.move_agents ('priority' | 'block_both' | 'soft'), _revert_action
+//   grid.py :: Grid.move, move_without_checks, on_goal, hide_agent
+//   envs.py :: Pogema.step, PogemaLifeLong.step, PogemaCoopFinish.step, update_was_on_goal
+//   generator.py :: generate_new_target (numpy Generator.choice on PCG64)
+//   wrappers/multi_time_limit.py :: MultiTimeLimit.step
+//   wrappers/metrics.py (raw counters only)
+//   envs.py :: _get_agents_obs; grid.py :: get_obstacles_for_agent, get_positions, get_square_target
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pgm_rng.h"
+
+namespace pgm {
+
+enum { OP_STEP = 0, OP_OBSERVE = 1, OP_RESET = 2 };
+enum { ST_FAIL = 0u, ST_OK = 1u, ST_PEND = 2u };
+constexpr uint32_t OCC_NONE = 0xFFFFu;
+
+struct StepArgs {
+  // geometry
+  int N, A, PH, PW, WPR, r, D;
+  int obst_stride;      // uint32 words per instance (multiple of 4, >= PH*WPR + 1)
+  int bits_per_agent;   // 3*D*D
+  int stage_bpa;        // stage bits per agent: bits_per_agent (U8) or rounded up to 32 (BITS)
+  int obs_format;       // 0 u8, 1 bits
+  int max_steps, auto_reset;
+  int on_target;        // 0 finish, 1 nothing, 2 restart
+  int batch_agents;     // agents per observation batch (stage capacity)
+  int max_rounds;       // pointer jumping round limit
+  // state
+  const uint32_t* obst;
+  uint32_t* pos;
+  uint32_t* tgt;
+  const uint32_t* pos0;
+  const uint32_t* tgt0;
+  uint8_t* active;
+  int32_t* elapsed;
+  Pcg64* rng;
+  const Pcg64* rng0;
+  const int32_t* comp_start;
+  const int32_t* comp_size;
+  const uint32_t* cells;
+  long long cells_stride;
+  uint8_t* was_on_goal;
+  uint8_t* episode_done;
+  int32_t* metric_acc;   // [N][4] running: solved, time_sum, cur_step, unused
+  int32_t* metric_last;  // [N][4] latched at episode end: solved, time_sum, steps, on_goal_now
+  // io
+  const uint8_t* actions;
+  int act_itemsize;
+  uint8_t* obs;
+  long long obs_inst_stride;  // bytes
+  float* rewards;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  int* err_flag;
+  // shared memory layout, byte offsets inside a team slice
+  int off_obst, off_abits, off_occ, off_pos, off_tgt, off_npos, off_link, off_act, off_flag, off_misc;
+  int team_smem;
+  int teams_per_cta;
+};
+
+// ------------------------------------------------------------------------- //
+// small PTX helpers
+// ------------------------------------------------------------------------- //
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+template <int TEAM>
+__device__ __forceinline__ void team_sync(int bar_id) {
+  if (TEAM == 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TEAM) : "memory");
+  }
+}
+// barrier + OR reduction over the team
+template <int TEAM>
+__device__ __forceinline__ bool team_any(int bar_id, bool p) {
+  if (TEAM == 32) {
+    __syncwarp();
+    return __any_sync(0xffffffffu, p);
+  } else {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred q, s;\n"
+        "setp.ne.u32 q, %2, 0;\n"
+        "barrier.red.or.pred s, %1, %3, q;\n"
+        "selp.u32 %0, 1, 0, s;\n"
+        "}"
+        : "=r"(r)
+        : "r"(bar_id), "r"((uint32_t)p), "n"(TEAM)
+        : "memory");
+    return r != 0;
+  }
+}
+
+__device__ __forceinline__ int opposite(int a) { return a == 0 ? 0 : (((a - 1) ^ 1) + 1); }  // 1<->2, 3<->4
+__device__ __forceinline__ int move_dx(int a) { return a == 1 ? -1 : (a == 2 ? 1 : 0); }
+__device__ __forceinline__ int move_dy(int a) { return a == 3 ? -1 : (a == 4 ? 1 : 0); }
+
+__device__ __forceinline__ uint32_t bit_at(const uint32_t* bits, int WPR, int x, int y) {
+  return (bits[x * WPR + (y >> 5)] >> (y & 31)) & 1u;
+}
+
+// Is some agent other than the one standing on (sx,sy) heading into (tx,ty)?
+// kind 0: any claimant;  kind 1: a claimant with lo < index < hi.
+template <int KIND>
+__device__ __forceinline__ bool other_claimant(const uint16_t* occ, const uint8_t* act, int PW, int tx, int ty,
+                                               int sx, int sy, int lo, int hi) {
+  bool found = false;
+#pragma unroll
+  for (int m = 1; m <= 4; ++m) {
+    int nx = tx + move_dx(m), ny = ty + move_dy(m);
+    if (nx == sx && ny == sy) continue;
+    uint32_t k = occ[nx * PW + ny];
+    if (k != OCC_NONE && act[k] == opposite(m)) {
+      if (KIND == 0) found = true;
+      else if ((int)k > lo && (int)k < hi) found = true;
+    }
+  }
+  return found;
+}
+
+// 4 bits -> 4 bytes (bit i -> byte i, value 0/1)
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+// ------------------------------------------------------------------------- //
+// observation generation for one batch of agents [g0, g0+gcount)
+// ------------------------------------------------------------------------- //
+template <int TEAM>
+__device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int tid, int bar_id, const uint32_t* s_obst,
+                                                  const uint32_t* s_abits, uint32_t* stage, const uint32_t* s_npos,
+                                                  const uint32_t* s_tgt) {
+  const int r = p.r, D = p.D, WPR = p.WPR;
+  const int bpa = p.bits_per_agent, sbpa = p.stage_bpa;
+  for (int g0 = 0; g0 < p.A; g0 += p.batch_agents) {
+    const int gcount = min(p.batch_agents, p.A - g0);
+    const int nbits = gcount * sbpa;
+    const int nwords = (nbits + 31) / 32 + 1;
+    for (int w = tid; w < nwords; w += TEAM) stage[w] = 0u;
+    team_sync<TEAM>(bar_id);
+    // ---- per agent: stream channel 0 (obstacles) and 1 (agents) row windows, set the target bit
+    for (int s = tid; s < gcount; s += TEAM) {
+      const int a = g0 + s;
+      const uint32_t pp = s_npos[a];
+      const int x = pp & 0xFFFF, y = pp >> 16;
+      uint32_t bitpos = (uint32_t)s * (uint32_t)sbpa;
+      uint32_t widx = bitpos >> 5;
+      uint32_t fill = bitpos & 31u;
+      unsigned long long acc = 0ull;
+      bool first = true;
+      const int y0 = y - r;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t* rows = (ch == 0 ? s_obst : s_abits) + (x - r) * WPR;
+#pragma unroll 1
+        for (int k = 0; k < D; ++k, rows += WPR) {
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            const int nb = min(32, D - c0);
+            const int yy = y0 + c0;
+            const int w = yy >> 5, sh = yy & 31;
+            uint32_t v = __funnelshift_r(rows[w], rows[w + 1], sh);
+            if (nb < 32) v &= (1u << nb) - 1u;
+            acc |= (unsigned long long)v << fill;
+            fill += nb;
+            if (fill >= 32u) {
+              if (first) {
+                atomicOr(&stage[widx], (uint32_t)acc);
+                first = false;
+              } else {
+                stage[widx] = (uint32_t)acc;
+              }
+              widx++;
+              acc >>= 32;
+              fill -= 32u;
+            }
+          }
+        }
+      }
+      if (fill > 0u) atomicOr(&stage[widx], (uint32_t)acc);
+      // channel 2: upstream grid.py :: get_square_target (clamped projection)
+      const uint32_t tt = s_tgt[a];
+      int dx = x - (int)(tt & 0xFFFF), dy = y - (int)(tt >> 16);
+      dx = max(-r, min(r, dx));
+      dy = max(-r, min(r, dy));
+      const uint32_t tb = (uint32_t)s * (uint32_t)sbpa + 2u * D * D + (uint32_t)(r - dx) * D + (uint32_t)(r - dy);
+      atomicOr(&stage[tb >> 5], 1u << (tb & 31u));
+    }
+    team_sync<TEAM>(bar_id);
+    // ---- write out
+    if (p.obs_format == 1) {
+      const int wpa = sbpa >> 5;
+      uint32_t* out = reinterpret_cast<uint32_t*>(p.obs + (long long)n * p.obs_inst_stride) + (long long)g0 * wpa;
+      for (int w = tid; w < gcount * wpa; w += TEAM) __stcs(out + w, stage[w]);
+    } else {
+      uint8_t* out = p.obs + (long long)n * p.obs_inst_stride + (long long)g0 * bpa;
+      const int nbytes = gcount * bpa;
+      int head = (int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
+      head = min(head, nbytes);
+      const int chunks = (nbytes - head) >> 4;
+      uint4* out16 = reinterpret_cast<uint4*>(out + head);
+      for (int c = tid; c < chunks; c += TEAM) {
+        const uint32_t bit = (uint32_t)head + ((uint32_t)c << 4);
+        const uint32_t w = bit >> 5, sh = bit & 31u;
+        const uint32_t v = __funnelshift_r(stage[w], stage[w + 1], sh);
+        uint4 o;
+        o.x = expand4(v & 15u);
+        o.y = expand4((v >> 4) & 15u);
+        o.z = expand4((v >> 8) & 15u);
+        o.w = expand4((v >> 12) & 15u);
+        __stcs(out16 + c, o);
+      }
+      const int tail0 = head + (chunks << 4);
+      for (int b = tid; b < head + (nbytes - tail0); b += TEAM) {
+        const int bb = b < head ? b : tail0 + (b - head);
+        out[bb] = (uint8_t)((stage[bb >> 5] >> (bb & 31)) & 1u);
+      }
+    }
+    if (g0 + p.batch_agents < p.A) team_sync<TEAM>(bar_id);
+  }
+}
+
+// ------------------------------------------------------------------------- //
+// the fused step kernel
+// ------------------------------------------------------------------------- //
+template <int TEAM, int COLL, int OP>
+__global__ void __launch_bounds__(1024) pgm_step_kernel(const StepArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int team = threadIdx.x / TEAM;
+  const int tid = threadIdx.x % TEAM;
+  const int n = blockIdx.x * p.teams_per_cta + team;
+  if (n >= p.N) return;  // whole team leaves together
+  const int bar_id = 1 + team;
+  unsigned char* base = smem_raw + (size_t)team * p.team_smem;
+  uint32_t* s_obst = reinterpret_cast<uint32_t*>(base + p.off_obst);
+  uint32_t* s_abits = reinterpret_cast<uint32_t*>(base + p.off_abits);
+  uint16_t* s_occ = reinterpret_cast<uint16_t*>(base + p.off_occ);
+  uint32_t* s_stage = reinterpret_cast<uint32_t*>(base + p.off_occ);  // aliases occ
+  uint32_t* s_pos = reinterpret_cast<uint32_t*>(base + p.off_pos);
+  uint32_t* s_tgt = reinterpret_cast<uint32_t*>(base + p.off_tgt);
+  uint32_t* s_npos = reinterpret_cast<uint32_t*>(base + p.off_npos);
+  uint32_t* s_link = reinterpret_cast<uint32_t*>(base + p.off_link);
+  uint8_t* s_act = base + p.off_act;
+  uint8_t* s_flag = base + p.off_flag;  // bit0 active, bit1 on_goal(after move), bit2 was_on_goal
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(base + p.off_misc);
+  int* s_cnt = reinterpret_cast<int*>(base + p.off_misc + 8);  // [0] on_goal count [1] was_on_goal count
+
+  const int A = p.A, PW = p.PW, WPR = p.WPR;
+  const int ONTGT = p.on_target;
+  const long long ia = (long long)n * A;
+
+  // ---- phase 0: obstacle map by bulk copy; state into shared memory -------
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_mbar_init();
+    s_cnt[0] = 0;
+    s_cnt[1] = 0;
+    const uint32_t bytes = (uint32_t)p.obst_stride * 4u;
+    mbar_expect_tx(s_bar, bytes);
+    bulk_g2s(s_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
+  }
+  const int grid_words = p.PH * WPR + 1;
+  for (int w = tid; w < grid_words; w += TEAM) s_abits[w] = 0u;
+  if (OP == OP_STEP) {
+    const int occ_words = (p.PH * PW + 1) >> 1;
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(s_occ);
+    for (int w = tid; w < occ_words; w += TEAM) o32[w] = 0xFFFFFFFFu;
+  }
+  for (int a = tid; a < A; a += TEAM) {
+    uint32_t pp, tt;
+    uint8_t fl;
+    if (OP == OP_RESET) {
+      pp = p.pos0[ia + a];
+      tt = p.tgt0[ia + a];
+      fl = 1;
+    } else {
+      pp = p.pos[ia + a];
+      tt = p.tgt[ia + a];
+      fl = p.active[ia + a] & 1u;
+    }
+    s_pos[a] = pp;
+    s_npos[a] = pp;
+    s_tgt[a] = tt;
+    s_flag[a] = fl;
+    if (OP == OP_STEP) {
+      uint32_t act = p.actions[(ia + a) * p.act_itemsize];
+      if (act > 4u) {
+        atomicOr(p.err_flag, 1);
+        act = 0u;
+      }
+      s_act[a] = (uint8_t)act;
+    }
+  }
+  team_sync<TEAM>(bar_id);
+
+  if (OP == OP_STEP) {
+    // ---- phase 1: pre-move occupancy grid (active agents only) ------------
+    for (int a = tid; a < A; a += TEAM) {
+      if (s_flag[a] & 1u) {
+        const uint32_t pp = s_pos[a];
+        s_occ[(pp & 0xFFFF) * PW + (pp >> 16)] = (uint16_t)a;
+      }
+    }
+    team_sync<TEAM>(bar_id);
+    mbar_wait(s_bar, 0);
+
+    // ---- phase 2: move resolution -----------------------------------------
+    if (COLL == 2) {
+      // soft, pass A: moves into obstacles and edge swaps become 'stay'
+      for (int a = tid; a < A; a += TEAM) {
+        uint32_t eff = 0u;
+        const uint32_t act = s_act[a];
+        if ((s_flag[a] & 1u) && act != 0u) {
+          const uint32_t pp = s_pos[a];
+          const int tx = (int)(pp & 0xFFFF) + move_dx(act), ty = (int)(pp >> 16) + move_dy(act);
+          eff = act;
+          if (bit_at(s_obst, WPR, tx, ty)) {
+            eff = 0u;
+          } else {
+            const uint32_t j = s_occ[tx * PW + ty];
+            if (j != OCC_NONE && s_act[j] == opposite(act)) eff = 0u;
+          }
+        }
+        s_link[a] = eff;  // temporarily: effective action
+      }
+      team_sync<TEAM>(bar_id);
+      // the effective actions replace the raw ones (each thread rewrites its own entries)
+      for (int a = tid; a < A; a += TEAM) s_act[a] = (uint8_t)s_link[a];
+      team_sync<TEAM>(bar_id);
+    }
+    bool pend = false;
+    for (int a = tid; a < A; a += TEAM) {
+      uint32_t link = ST_FAIL;
+      const uint32_t act = s_act[a];
+      if ((s_flag[a] & 1u) && act != 0u) {
+        const uint32_t pp = s_pos[a];
+        const int sx = pp & 0xFFFF, sy = pp >> 16;
+        const int tx = sx + move_dx(act), ty = sy + move_dy(act);
+        if (!bit_at(s_obst, WPR, tx, ty)) {
+          const uint32_t j = s_occ[tx * PW + ty];
+          if (COLL == 1) {
+            // block_both: free cell, sole claimant
+            if (j == OCC_NONE && !other_claimant<0>(s_occ, s_act, PW, tx, ty, sx, sy, 0, 0)) link = ST_OK;
+          } else if (COLL == 0) {
+            // priority: occupant must have a lower index and leave; first claimant above it wins
+            bool ok = true;
+            int lo = -1;
+            if (j != OCC_NONE) {
+              if ((int)j > a || s_act[j] == 0) ok = false;
+              else lo = (int)j;
+            }
+            if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, lo, a)) ok = false;
+            if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
+          } else {
+            // soft: no stayer on the cell, lowest-index claimant, occupant must leave
+            bool ok = !(j != OCC_NONE && s_act[j] == 0);
+            if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, -1, a)) ok = false;
+            if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
+          }
+        }
+      }
+      s_link[a] = link;
+      pend |= ((link & 3u) == ST_PEND);
+    }
+    if (COLL != 1) {
+      // pointer jumping along occupant chains; what is still pending after
+      // max_rounds is a rotation cycle (soft only) and succeeds
+      int rounds = 0;
+      while (team_any<TEAM>(bar_id, pend)) {
+        if (++rounds > p.max_rounds) break;
+        pend = false;
+        for (int a = tid; a < A; a += TEAM) {
+          const uint32_t l = s_link[a];
+          if ((l & 3u) == ST_PEND) {
+            const uint32_t lp = s_link[l >> 2];
+            const uint32_t nl = ((lp & 3u) == ST_PEND) ? (ST_PEND | (lp & ~3u)) : (lp & 3u);
+            s_link[a] = nl;
+            pend |= ((nl & 3u) == ST_PEND);
+          }
+        }
+      }
+    }
+    team_sync<TEAM>(bar_id);
+
+    // ---- phase 3: apply moves, on_target bookkeeping, time limit -----------
+    int c_on = 0, c_was = 0;
+    for (int a = tid; a < A; a += TEAM) {
+      const uint32_t act = s_act[a];
+      uint32_t pp = s_pos[a];
+      if ((s_link[a] & 3u) != ST_FAIL) {
+        const int tx = (int)(pp & 0xFFFF) + move_dx(act), ty = (int)(pp >> 16) + move_dy(act);
+        pp = (uint32_t)tx | ((uint32_t)ty << 16);
+      }
+      s_npos[a] = pp;
+      const uint32_t on = (pp == s_tgt[a]) ? 1u : 0u;
+      const uint32_t fl = s_flag[a] & 1u;
+      const uint32_t was = on & fl;
+      s_flag[a] = (uint8_t)(fl | (on << 1) | (was << 2));
+      c_on += on;
+      c_was += was;
+    }
+    c_on = __reduce_add_sync(0xffffffffu, c_on);
+    c_was = __reduce_add_sync(0xffffffffu, c_was);
+    if ((threadIdx.x & 31) == 0) {
+      if (TEAM == 32) {
+        s_cnt[0] = c_on;
+        s_cnt[1] = c_was;
+      } else {
+        atomicAdd(&s_cnt[0], c_on);
+        atomicAdd(&s_cnt[1], c_was);
+      }
+    }
+    team_sync<TEAM>(bar_id);  // also: every read of occ is done -> stage may reuse it
+    c_on = s_cnt[0];
+    c_was = s_cnt[1];
+    const int step_idx = p.elapsed[n];
+    const bool trunc = (step_idx + 1 >= p.max_steps);
+    const bool solved = (c_was == A);
+    const bool all_term = (ONTGT == 2) ? false : (c_on == A);
+    const bool done = trunc || all_term;
+    const bool do_reset = done && p.auto_reset;
+
+    for (int a = tid; a < A; a += TEAM) {
+      const uint32_t f = s_flag[a];
+      const uint32_t fl = f & 1u, on = (f >> 1) & 1u, was = (f >> 2) & 1u;
+      float rew;
+      uint8_t term;
+      uint32_t nfl = fl;
+      uint32_t tt = s_tgt[a];
+      if (ONTGT == 0) {  // finish: reward once, agent disappears
+        rew = was ? 1.0f : 0.0f;
+        term = (uint8_t)on;
+        nfl = fl & (on ^ 1u);
+      } else if (ONTGT == 1) {  // nothing (cooperative finish)
+        rew = solved ? 1.0f : 0.0f;
+        term = solved ? 1 : 0;
+      } else {  // restart (lifelong): new target from the agent's own generator
+        rew = was ? 1.0f : 0.0f;
+        term = 0;
+        if (on && !do_reset) {
+          Pcg64 g = p.rng[ia + a];
+          const uint32_t k = pcg64_bounded32(g, (uint32_t)(p.comp_size[ia + a] - 1));
+          tt = p.cells[(long long)n * p.cells_stride + p.comp_start[ia + a] + k];
+          p.rng[ia + a] = g;
+        }
+      }
+      p.rewards[ia + a] = rew;
+      p.terminated[ia + a] = term;
+      p.truncated[ia + a] = trunc ? 1 : 0;
+      p.was_on_goal[ia + a] = (uint8_t)was;
+      uint32_t pp = s_npos[a];
+      if (do_reset) {
+        pp = p.pos0[ia + a];
+        tt = p.tgt0[ia + a];
+        nfl = 1u;
+        if (ONTGT == 2) p.rng[ia + a] = p.rng0[ia + a];
+      }
+      s_npos[a] = pp;
+      s_tgt[a] = tt;
+      s_flag[a] = (uint8_t)nfl;
+      p.pos[ia + a] = pp;
+      p.tgt[ia + a] = tt;
+      p.active[ia + a] = (uint8_t)nfl;
+    }
+    if (tid == 0) {
+      p.elapsed[n] = do_reset ? 0 : step_idx + 1;
+      p.episode_done[n] = done ? 1 : 0;
+      // raw counters of upstream wrappers/metrics.py
+      int32_t* acc = p.metric_acc + 4 * (long long)n;
+      const int mstep = acc[2];
+      const int solved_sum = acc[0] + c_was;
+      const int time_sum = acc[1] + c_was * mstep;
+      if (done) {
+        int32_t* last = p.metric_last + 4 * (long long)n;
+        last[0] = solved_sum;
+        last[1] = time_sum + (A - solved_sum) * mstep;
+        last[2] = mstep + 1;
+        last[3] = c_was;
+        acc[0] = 0;
+        acc[1] = 0;
+        acc[2] = 0;
+      } else {
+        acc[0] = solved_sum;
+        acc[1] = time_sum;
+        acc[2] = mstep + 1;
+      }
+    }
+  } else {
+    if (OP == OP_RESET) {
+      for (int a = tid; a < A; a += TEAM) {
+        p.pos[ia + a] = s_pos[a];
+        p.tgt[ia + a] = s_tgt[a];
+        p.active[ia + a] = 1;
+        p.was_on_goal[ia + a] = (s_pos[a] == s_tgt[a]) ? 1 : 0;
+        if (ONTGT == 2) p.rng[ia + a] = p.rng0[ia + a];
+      }
+      if (tid == 0) {
+        p.elapsed[n] = 0;
+        p.episode_done[n] = 0;
+        int32_t* acc = p.metric_acc + 4 * (long long)n;
+        acc[0] = acc[1] = acc[2] = acc[3] = 0;
+      }
+    }
+    mbar_wait(s_bar, 0);
+  }
+
+  if (p.obs == nullptr) return;
+  // ---- phase 4: post-move agent bitmap -------------------------------------
+  for (int a = tid; a < A; a += TEAM) {
+    if (s_flag[a] & 1u) {
+      const uint32_t pp = s_npos[a];
+      const int x = pp & 0xFFFF, y = pp >> 16;
+      atomicOr(&s_abits[x * WPR + (y >> 5)], 1u << (y & 31));
+    }
+  }
+  // (emit_observations starts with stage zeroing + team_sync, which also orders the atomics)
+  // ---- phase 5: observations -------------------------------------------------
+  emit_observations<TEAM>(p, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
+}
+
+}  // namespace pgm

@@ -1,0 +1,111 @@
+"""GPU parity: the CUDA step engine (through the C-ABI, via BatchedPogema) against
+the CPU oracle on identical seeds and action streams - bit-exact on positions,
+targets, active flags, rewards, terminated, truncated and every observation byte."""
+import itertools
+
+import numpy as np
+import pytest
+
+from tests.helpers import make_actions, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+COLLISIONS = ("priority", "block_both", "soft")
+ON_TARGETS = ("finish", "nothing", "restart")
+
+
+def run_gpu(gc_kwargs, seeds, actions, auto_reset=False, obs_format="u8", team_threads=0):
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    env = BatchedPogema(GridConfig(**gc_kwargs), num_envs=len(seeds), seeds=seeds, auto_reset=auto_reset,
+                        obs_format=obs_format, team_threads=team_threads)
+    out = {k: [] for k in ("obs", "pos", "tgt", "active", "rewards", "terminated", "truncated")}
+
+    def snap(o):
+        out["obs"].append(o.cpu().numpy().copy())
+        out["pos"].append(env.get_agents_xy().cpu().numpy())
+        out["tgt"].append(env.get_targets_xy().cpu().numpy())
+        out["active"].append(env.is_active.cpu().numpy().astype(np.uint8))
+
+    snap(env.reset())
+    for t in range(actions.shape[0]):
+        o, r, te, tr = env.step(torch.from_numpy(actions[t]).cuda())
+        snap(o)
+        out["rewards"].append(r.cpu().numpy().copy())
+        out["terminated"].append(te.cpu().numpy().copy())
+        out["truncated"].append(tr.cpu().numpy().copy())
+    env.check_errors()
+    res = {k: np.stack(v) for k, v in out.items()}
+    res["env"] = env
+    return res
+
+
+def compare(gc_kwargs, seeds, T, auto_reset=False, team_threads=0, action_seed=7):
+    A = gc_kwargs["num_agents"]
+    actions = make_actions(T, len(seeds), A, seed=action_seed)
+    gpu = run_gpu(gc_kwargs, seeds, actions, auto_reset=auto_reset, team_threads=team_threads)
+    for k, seed in enumerate(seeds):
+        ref = run_oracle(gc_kwargs, seed, actions[:, k], auto_reset=auto_reset)
+        for key in ("pos", "tgt", "active", "obs"):
+            g = gpu[key][:, k]
+            assert g.shape == ref[key].shape, (key, g.shape, ref[key].shape)
+            if not np.array_equal(g, ref[key]):
+                t = int(np.argmax([not np.array_equal(g[i], ref[key][i]) for i in range(g.shape[0])]))
+                raise AssertionError(f"{key} differs: instance {k} seed {seed} first at t={t}\n"
+                                     f"gpu={g[t].tolist() if key != 'obs' else 'obs'}\nref={ref[key][t].tolist() if key != 'obs' else 'obs'}\n"
+                                     f"cfg={gc_kwargs}")
+        for key in ("rewards", "terminated", "truncated"):
+            g = gpu[key][:, k]
+            assert np.array_equal(g, ref[key]), (key, k, seed, gc_kwargs)
+    return gpu
+
+
+@pytest.mark.parametrize("coll,ot", list(itertools.product(COLLISIONS, ON_TARGETS)))
+def test_all_modes_small(coll, ot):
+    """BASELINE.json configs[0] shape (8x8, 4 agents, r=5) for all 9 mode combinations."""
+    gc = dict(size=8, density=0.3, num_agents=4, obs_radius=5, max_episode_steps=64, collision_system=coll,
+              on_target=ot)
+    compare(gc, seeds=list(range(16)), T=70)
+
+
+@pytest.mark.parametrize("coll,ot", list(itertools.product(COLLISIONS, ON_TARGETS)))
+def test_all_modes_crowded(coll, ot):
+    """Crowded 10x10 maps: many conflicts, chains and rotations."""
+    gc = dict(size=10, density=0.1, num_agents=40, obs_radius=3, max_episode_steps=32, collision_system=coll,
+              on_target=ot)
+    compare(gc, seeds=list(range(100, 124)), T=40)
+
+
+@pytest.mark.parametrize("coll,ot", list(itertools.product(COLLISIONS, ON_TARGETS)))
+def test_all_modes_autoreset(coll, ot):
+    gc = dict(size=8, density=0.2, num_agents=6, obs_radius=2, max_episode_steps=10, collision_system=coll,
+              on_target=ot)
+    compare(gc, seeds=list(range(8)), T=35, auto_reset=True)
+
+
+@pytest.mark.parametrize("team", [32, 64, 128, 256])
+def test_config2_shape_team_sizes(team):
+    """BASELINE.json configs[1] instance shape (32x32, 64 agents, r=5, priority/finish), few instances."""
+    gc = dict(size=32, density=0.3, num_agents=64, obs_radius=5, max_episode_steps=64,
+              collision_system="priority", on_target="finish")
+    compare(gc, seeds=list(range(6)), T=66, team_threads=team)
+
+
+@pytest.mark.parametrize("r", [1, 2, 3, 5, 7, 10, 16, 20])
+def test_obs_radius_sweep(r):
+    gc = dict(size=12, density=0.25, num_agents=9, obs_radius=r, max_episode_steps=16,
+              collision_system="soft", on_target="restart")
+    compare(gc, seeds=list(range(5)), T=20)
+
+
+def test_lifelong_64x64():
+    """BASELINE.json configs[2] shape, scaled down in instance count (random maps; maze maps in test_maps)."""
+    gc = dict(size=64, density=0.3, num_agents=256, obs_radius=5, max_episode_steps=64,
+              collision_system="soft", on_target="restart")
+    compare(gc, seeds=[0, 1], T=40)
+
+
+def test_block_both_many_agents():
+    gc = dict(size=48, density=0.2, num_agents=600, obs_radius=5, max_episode_steps=32,
+              collision_system="block_both", on_target="finish")
+    compare(gc, seeds=[3], T=24)
