@@ -3,15 +3,27 @@ NVCC ?= nvcc
 CXX ?= g++
 CC ?= gcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O3,-Wall
 CSRC := pogema_b200/csrc
+BUILD := build
 LIB := pogema_b200/_lib/libpgm_b200.so
+CU := pgm_capi pgm_inst_step_priority pgm_inst_step_block_both pgm_inst_step_soft pgm_inst_observe pgm_inst_reset
+OBJS := $(addprefix $(BUILD)/,$(addsuffix .o,$(CU))) $(BUILD)/pgm_gen.o
+HDRS := $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h include/pgm_b200.h
 
 all: $(LIB) oracle
 
-$(LIB): $(CSRC)/pgm_capi.cu $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.cpp $(CSRC)/pgm_gen.h include/pgm_b200.h
-	mkdir -p pogema_b200/_lib
-	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -Xptxas -v -Xcompiler -fPIC,-O3,-Wall -shared \
-	    $(CSRC)/pgm_capi.cu $(CSRC)/pgm_gen.cpp -o $(LIB) -lpthread
+$(BUILD)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) $(PTXAS_V) -c $< -o $@
+
+$(BUILD)/pgm_gen.o: $(CSRC)/pgm_gen.cpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p pogema_b200/_lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lpthread
 
 oracle: oracle/liboracle_step.so
 
@@ -19,6 +31,6 @@ oracle/liboracle_step.so: oracle/step_oracle.c
 	$(CC) -O2 -fPIC -shared -Wall -o $@ $< -lm
 
 clean:
-	rm -f $(LIB) oracle/liboracle_step.so
+	rm -rf $(BUILD) $(LIB) oracle/liboracle_step.so
 
 .PHONY: all oracle clean

@@ -55,9 +55,11 @@ enum {
 };
 /* pgm_get_state / pgm_state_ptr selectors */
 enum {
-  PGM_STATE_POSITIONS = 0, /* int32 [N][A][2] unpadded (x,y)  (host copy) / packed u32 (device)  */
-  PGM_STATE_TARGETS = 1,   /* int32 [N][A][2]                                                    */
-  PGM_STATE_ACTIVE = 2,    /* uint8 [N][A]   upstream grid.py :: Grid.is_active                  */
+  PGM_STATE_POSITIONS = 0, /* host copy: int32 [N][A][2] unpadded (x,y).  pgm_state_ptr: the raw
+                              agent state array uint32 [N][A][2]: word 0 = (x+r) | active << 15 |
+                              (y+r) << 16, word 1 = (tx+r) | (ty+r) << 16                         */
+  PGM_STATE_TARGETS = 1,   /* int32 [N][A][2] unpadded (host copy only)                          */
+  PGM_STATE_ACTIVE = 2,    /* uint8 [N][A]   upstream grid.py :: Grid.is_active (host copy only) */
   PGM_STATE_ELAPSED = 3,   /* int32 [N]      upstream MultiTimeLimit._elapsed_steps              */
   PGM_STATE_OBSTACLES = 4, /* uint8 [N][H][W] unpadded (host copy only)                          */
   PGM_STATE_WAS_ON_GOAL = 5,/* uint8 [N][A]  upstream envs.py :: Pogema.was_on_goal (last step)  */

@@ -120,9 +120,13 @@ class BatchedPogema:
         ptr = self.engine.state_ptr(what)
         return torch.as_tensor(_DevArray(ptr, shape, typestr, self), device=self.device)
 
+    def _state(self) -> torch.Tensor:
+        """Raw agent state words int32 [N, A, 2] (include/pgm_b200.h, PGM_STATE_POSITIONS)."""
+        return self._view(nat.STATE_POSITIONS, (self.num_envs, self.num_agents, 2), "<i4")
+
     @property
     def is_active(self) -> torch.Tensor:
-        return self._view(nat.STATE_ACTIVE, (self.num_envs, self.num_agents), "|u1").bool()
+        return ((self._state()[..., 0] >> 15) & 1).bool()
 
     @property
     def was_on_goal(self) -> torch.Tensor:
@@ -136,17 +140,16 @@ class BatchedPogema:
     def elapsed_steps(self) -> torch.Tensor:
         return self._view(nat.STATE_ELAPSED, (self.num_envs,), "<i4")
 
-    def _xy(self, what) -> torch.Tensor:
-        packed = self._view(what, (self.num_envs, self.num_agents), "<i4")
-        r = self.grid_config.obs_radius
-        return torch.stack(((packed & 0xFFFF) - r, (packed >> 16) - r), dim=-1)
-
     def get_agents_xy(self) -> torch.Tensor:
         """int32 [N, A, 2] unpadded (x, y) positions."""
-        return self._xy(nat.STATE_POSITIONS)
+        w = self._state()[..., 0]
+        r = self.grid_config.obs_radius
+        return torch.stack(((w & 0x7FFF) - r, ((w >> 16) & 0xFFFF) - r), dim=-1)
 
     def get_targets_xy(self) -> torch.Tensor:
-        return self._xy(nat.STATE_TARGETS)
+        w = self._state()[..., 1]
+        r = self.grid_config.obs_radius
+        return torch.stack(((w & 0x7FFF) - r, ((w >> 16) & 0xFFFF) - r), dim=-1)
 
     def get_obstacles(self) -> np.ndarray:
         """uint8 [N, H, W] unpadded obstacle maps (host array)."""

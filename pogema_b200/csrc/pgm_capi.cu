@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -12,7 +13,7 @@
 
 #include "../../include/pgm_b200.h"
 #include "pgm_gen.h"
-#include "pgm_kernels.cuh"
+#include "pgm_launch.cuh"
 
 using namespace pgm;
 
@@ -65,8 +66,9 @@ struct pgm_engine {
   int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1;
   StepArgs layout{};  // offsets only
   // device state
-  uint32_t *d_obst = nullptr, *d_pos = nullptr, *d_tgt = nullptr, *d_pos0 = nullptr, *d_tgt0 = nullptr;
-  uint8_t *d_active = nullptr, *d_was = nullptr, *d_done = nullptr;
+  uint32_t* d_obst = nullptr;
+  uint2 *d_state = nullptr, *d_state0 = nullptr;  // see pgm_kernels.cuh: x | active<<15 | y<<16 , target
+  uint8_t *d_was = nullptr, *d_done = nullptr;
   int32_t *d_elapsed = nullptr, *d_macc = nullptr, *d_mlast = nullptr;
   Pcg64 *d_rng = nullptr, *d_rng0 = nullptr;
   int32_t *d_cstart = nullptr, *d_csize = nullptr;
@@ -79,6 +81,7 @@ struct pgm_engine {
   // host mirrors
   std::vector<uint32_t> h_obst;
   int64_t launches = 0;
+  bool use_pdl = true;
 };
 
 namespace {
@@ -150,42 +153,20 @@ int compute_plan(pgm_engine* e) {
   return PGM_OK;
 }
 
-template <int TEAM, int COLL, int OP>
-int launch_one(pgm_engine* e, const StepArgs& a, cudaStream_t s) {
-  auto kern = pgm_step_kernel<TEAM, COLL, OP>;
-  static thread_local int configured_dev = -1;
-  static thread_local int configured_smem = -1;
-  if (configured_dev != e->cfg.device || configured_smem < e->smem_cta) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_cta));
-    configured_dev = e->cfg.device;
-    configured_smem = e->smem_cta;
-  }
-  kern<<<e->grid, e->cta_threads, e->smem_cta, s>>>(a);
-  CUDA_TRY(cudaGetLastError());
+int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
+  LaunchDims d{e->team, static_radius(e->cfg.obs_radius), e->grid, e->cta_threads, e->smem_cta, e->cfg.device,
+               e->use_pdl ? 1 : 0};
+  int err;
+  if (op == OP_OBSERVE) err = launch_observe(d, a, s);
+  else if (op == OP_RESET) err = launch_reset(d, a, s);
+  else if (e->cfg.collision_system == PGM_COLLISION_PRIORITY) err = launch_step_priority(d, a, s);
+  else if (e->cfg.collision_system == PGM_COLLISION_BLOCK_BOTH) err = launch_step_block_both(d, a, s);
+  else err = launch_step_soft(d, a, s);
+  if (err != 0)
+    return fail(PGM_ERR_CUDA, "kernel launch failed: %s (grid %d, block %d, smem %d)",
+                cudaGetErrorString((cudaError_t)err), d.grid, d.block, d.smem);
   e->launches++;
   return PGM_OK;
-}
-
-template <int TEAM>
-int launch_team(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
-  if (op == OP_OBSERVE) return launch_one<TEAM, 0, OP_OBSERVE>(e, a, s);
-  if (op == OP_RESET) return launch_one<TEAM, 0, OP_RESET>(e, a, s);
-  switch (e->cfg.collision_system) {
-    case PGM_COLLISION_PRIORITY: return launch_one<TEAM, 0, OP_STEP>(e, a, s);
-    case PGM_COLLISION_BLOCK_BOTH: return launch_one<TEAM, 1, OP_STEP>(e, a, s);
-    default: return launch_one<TEAM, 2, OP_STEP>(e, a, s);
-  }
-}
-
-int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
-  switch (e->team) {
-    case 32: return launch_team<32>(e, a, op, s);
-    case 64: return launch_team<64>(e, a, op, s);
-    case 128: return launch_team<128>(e, a, op, s);
-    case 256: return launch_team<256>(e, a, op, s);
-    case 512: return launch_team<512>(e, a, op, s);
-    default: return launch_team<1024>(e, a, op, s);
-  }
 }
 
 StepArgs make_args(pgm_engine* e) {
@@ -210,11 +191,8 @@ StepArgs make_args(pgm_engine* e) {
   while ((1 << lg) < c.num_agents) lg++;
   a.max_rounds = lg + 2;
   a.obst = e->d_obst;
-  a.pos = e->d_pos;
-  a.tgt = e->d_tgt;
-  a.pos0 = e->d_pos0;
-  a.tgt0 = e->d_tgt0;
-  a.active = e->d_active;
+  a.state = e->d_state;
+  a.state0 = e->d_state0;
   a.elapsed = e->d_elapsed;
   a.rng = e->d_rng;
   a.rng0 = e->d_rng0;
@@ -252,20 +230,17 @@ struct DeviceGuard {
 // Upload generated instances [first, first+count) and make them the current state.
 int upload_instances(pgm_engine* e, int first, int count, std::vector<GenInstance>& inst, cudaStream_t s) {
   const int A = e->cfg.num_agents;
-  std::vector<uint32_t> obst((size_t)count * e->obst_stride, 0u), pos((size_t)count * A), tgt((size_t)count * A);
+  std::vector<uint32_t> obst((size_t)count * e->obst_stride, 0u);
+  std::vector<uint2> st((size_t)count * A);
   for (int k = 0; k < count; ++k) {
     memcpy(&obst[(size_t)k * e->obst_stride], inst[k].obst_bits.data(), inst[k].obst_bits.size() * 4);
-    memcpy(&pos[(size_t)k * A], inst[k].pos.data(), (size_t)A * 4);
-    memcpy(&tgt[(size_t)k * A], inst[k].tgt.data(), (size_t)A * 4);
+    for (int a = 0; a < A; ++a) st[(size_t)k * A + a] = make_uint2(inst[k].pos[a] | 0x8000u, inst[k].tgt[a]);
   }
   memcpy(&e->h_obst[(size_t)first * e->obst_stride], obst.data(), obst.size() * 4);
   CUDA_TRY(cudaMemcpyAsync(e->d_obst + (size_t)first * e->obst_stride, obst.data(), obst.size() * 4,
                            cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(e->d_pos0 + (size_t)first * A, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(e->d_tgt0 + (size_t)first * A, tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(e->d_pos + (size_t)first * A, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(e->d_tgt + (size_t)first * A, tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemsetAsync(e->d_active + (size_t)first * A, 1, (size_t)count * A, s));
+  CUDA_TRY(cudaMemcpyAsync(e->d_state0 + (size_t)first * A, st.data(), st.size() * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(e->d_state + (size_t)first * A, st.data(), st.size() * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemsetAsync(e->d_was + (size_t)first * A, 0, (size_t)count * A, s));
   CUDA_TRY(cudaMemsetAsync(e->d_done + first, 0, (size_t)count, s));
   CUDA_TRY(cudaMemsetAsync(e->d_elapsed + first, 0, (size_t)count * 4, s));
@@ -368,6 +343,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
   DeviceGuard guard(cfg->device);
   pgm_engine* e = new pgm_engine();
   e->cfg = *cfg;
+  if (const char* v = getenv("PGM_NO_PDL")) e->use_pdl = !(v[0] == '1');
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
   e->sm_count = prop.multiProcessorCount;
@@ -400,11 +376,8 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
     return rc;         \
   }
   TRY_ALLOC(dev_alloc(&e->d_obst, (size_t)N * e->obst_stride));
-  TRY_ALLOC(dev_alloc(&e->d_pos, (size_t)N * A));
-  TRY_ALLOC(dev_alloc(&e->d_tgt, (size_t)N * A));
-  TRY_ALLOC(dev_alloc(&e->d_pos0, (size_t)N * A));
-  TRY_ALLOC(dev_alloc(&e->d_tgt0, (size_t)N * A));
-  TRY_ALLOC(dev_alloc(&e->d_active, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_state, (size_t)N * A));
+  TRY_ALLOC(dev_alloc(&e->d_state0, (size_t)N * A));
   TRY_ALLOC(dev_alloc(&e->d_was, (size_t)N * A));
   TRY_ALLOC(dev_alloc(&e->d_done, (size_t)N));
   TRY_ALLOC(dev_alloc(&e->d_elapsed, (size_t)N));
@@ -427,7 +400,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
 int pgm_destroy(pgm_engine* e) {
   if (!e) return PGM_OK;
   DeviceGuard guard(e->cfg.device);
-  void* ptrs[] = {e->d_obst,  e->d_pos,   e->d_tgt,   e->d_pos0,   e->d_tgt0,  e->d_active, e->d_was,
+  void* ptrs[] = {e->d_obst,  e->d_state, e->d_state0, e->d_was,
                   e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
                   e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h, e->d_term_h, e->d_trunc_h,
                   e->d_rew_h};
@@ -609,24 +582,28 @@ int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, voi
   auto need = [&](int64_t n) { return dst_bytes >= n ? 0 : fail(PGM_ERR_INVALID, "destination too small: %lld < %lld", (long long)dst_bytes, (long long)n); };
   switch (what) {
     case PGM_STATE_POSITIONS:
-    case PGM_STATE_TARGETS: {
-      if (need(N * A * 8)) return PGM_ERR_INVALID;
-      std::vector<uint32_t> tmp((size_t)(N * A));
-      CUDA_TRY(cudaMemcpyAsync(tmp.data(), what == PGM_STATE_POSITIONS ? e->d_pos : e->d_tgt, tmp.size() * 4,
-                               cudaMemcpyDeviceToHost, s));
+    case PGM_STATE_TARGETS:
+    case PGM_STATE_ACTIVE: {
+      if (need(what == PGM_STATE_ACTIVE ? N * A : N * A * 8)) return PGM_ERR_INVALID;
+      std::vector<uint2> tmp((size_t)(N * A));
+      CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->d_state, tmp.size() * 8, cudaMemcpyDeviceToHost, s));
       CUDA_TRY(cudaStreamSynchronize(s));
-      int32_t* o = (int32_t*)dst;
-      for (size_t i = 0; i < tmp.size(); ++i) {
-        o[2 * i] = (int32_t)(tmp[i] & 0xFFFF) - (int32_t)r;
-        o[2 * i + 1] = (int32_t)(tmp[i] >> 16) - (int32_t)r;
+      if (what == PGM_STATE_ACTIVE) {
+        uint8_t* o = (uint8_t*)dst;
+        for (size_t i = 0; i < tmp.size(); ++i) o[i] = (tmp[i].x >> 15) & 1u;
+      } else {
+        int32_t* o = (int32_t*)dst;
+        for (size_t i = 0; i < tmp.size(); ++i) {
+          const uint32_t w = what == PGM_STATE_POSITIONS ? tmp[i].x : tmp[i].y;
+          o[2 * i] = (int32_t)(w & 0x7FFF) - (int32_t)r;
+          o[2 * i + 1] = (int32_t)(w >> 16) - (int32_t)r;
+        }
       }
       return PGM_OK;
     }
-    case PGM_STATE_ACTIVE:
     case PGM_STATE_WAS_ON_GOAL: {
       if (need(N * A)) return PGM_ERR_INVALID;
-      CUDA_TRY(cudaMemcpyAsync(dst, what == PGM_STATE_ACTIVE ? e->d_active : e->d_was, (size_t)(N * A),
-                               cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaMemcpyAsync(dst, e->d_was, (size_t)(N * A), cudaMemcpyDeviceToHost, s));
       CUDA_TRY(cudaStreamSynchronize(s));
       return PGM_OK;
     }
@@ -669,9 +646,7 @@ int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, voi
 void* pgm_state_ptr(pgm_engine* e, int32_t what) {
   if (!e) return nullptr;
   switch (what) {
-    case PGM_STATE_POSITIONS: return e->d_pos;
-    case PGM_STATE_TARGETS: return e->d_tgt;
-    case PGM_STATE_ACTIVE: return e->d_active;
+    case PGM_STATE_POSITIONS: return e->d_state;  // packed agent state words, see pgm_b200.h
     case PGM_STATE_ELAPSED: return e->d_elapsed;
     case PGM_STATE_WAS_ON_GOAL: return e->d_was;
     case PGM_STATE_EPISODE_DONE: return e->d_done;
@@ -683,7 +658,7 @@ void* pgm_state_ptr(pgm_engine* e, int32_t what) {
 int64_t pgm_checkpoint_bytes(const pgm_engine* e) {
   if (!e) return 0;
   const int64_t N = e->cfg.num_envs, A = e->cfg.num_agents;
-  int64_t b = N * A * (4 + 4 + 1 + 1) + N * (4 + 1 + 16 + 16);
+  int64_t b = N * A * (8 + 1) + N * (4 + 1 + 16 + 16);
   if (e->lifelong) b += N * A * (int64_t)sizeof(Pcg64);
   return b;
 }
@@ -695,8 +670,7 @@ struct CkptPart {
 };
 std::vector<CkptPart> ckpt_parts(pgm_engine* e) {
   const size_t N = e->cfg.num_envs, A = e->cfg.num_agents;
-  std::vector<CkptPart> v = {{e->d_pos, N * A * 4}, {e->d_tgt, N * A * 4},  {e->d_active, N * A},
-                             {e->d_was, N * A},     {e->d_elapsed, N * 4}, {e->d_done, N},
+  std::vector<CkptPart> v = {{e->d_state, N * A * 8}, {e->d_was, N * A},     {e->d_elapsed, N * 4}, {e->d_done, N},
                              {e->d_macc, N * 16},   {e->d_mlast, N * 16}};
   if (e->lifelong) v.push_back({e->d_rng, N * A * sizeof(Pcg64)});
   return v;

@@ -48,11 +48,8 @@ struct StepArgs {
   int max_rounds;       // pointer jumping round limit
   // state
   const uint32_t* obst;
-  uint32_t* pos;
-  uint32_t* tgt;
-  const uint32_t* pos0;
-  const uint32_t* tgt0;
-  uint8_t* active;
+  uint2* state;         // [N][A] .x = x | active << 15 | y << 16, .y = target x | y << 16  (padded coords)
+  const uint2* state0;  // initial task (auto reset / pgm_reset)
   int32_t* elapsed;
   Pcg64* rng;
   const Pcg64* rng0;
@@ -177,65 +174,138 @@ __device__ __forceinline__ bool other_claimant(const uint16_t* occ, const uint8_
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
 // ------------------------------------------------------------------------- //
-// observation generation for one batch of agents [g0, g0+gcount)
+// observation bits of ONE agent
 // ------------------------------------------------------------------------- //
-template <int TEAM>
+// Generic radius (runtime D): stream the row windows of channel 0 (obstacles)
+// and 1 (agents) into the stage bit stream at an arbitrary bit offset.
+__device__ __forceinline__ void agent_bits_generic(const StepArgs& p, const uint32_t* s_obst, const uint32_t* s_abits,
+                                                   uint32_t* stage, int x, int y, uint32_t bitpos) {
+  const int r = p.r, D = p.D, WPR = p.WPR;
+  uint32_t widx = bitpos >> 5;
+  uint32_t fill = bitpos & 31u;
+  unsigned long long acc = 0ull;
+  bool first = true;
+  const int y0 = y - r;
+#pragma unroll 1
+  for (int ch = 0; ch < 2; ++ch) {
+    const uint32_t* rows = (ch == 0 ? s_obst : s_abits) + (x - r) * WPR;
+#pragma unroll 1
+    for (int k = 0; k < D; ++k, rows += WPR) {
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        const int nb = min(32, D - c0);
+        const int yy = y0 + c0;
+        const int w = yy >> 5, sh = yy & 31;
+        uint32_t v = __funnelshift_r(rows[w], rows[w + 1], sh);
+        if (nb < 32) v &= (1u << nb) - 1u;
+        acc |= (unsigned long long)v << fill;
+        fill += nb;
+        if (fill >= 32u) {
+          if (first) {
+            atomicOr(&stage[widx], (uint32_t)acc);
+            first = false;
+          } else {
+            stage[widx] = (uint32_t)acc;
+          }
+          widx++;
+          acc >>= 32;
+          fill -= 32u;
+        }
+      }
+    }
+  }
+  if (fill > 0u) atomicOr(&stage[widx], (uint32_t)acc);
+}
+
+// Compile-time radius (D <= 32): the two occupancy channels are assembled in
+// registers at static bit offsets (fully unrolled), then stored to the stage
+// stream with one funnel shift per word.
+template <int D, int OFF>
+__device__ __forceinline__ void insert_bits(uint32_t (&acc)[(3 * D * D + 31) / 32], uint32_t v) {
+  constexpr int W = OFF >> 5, C = OFF & 31;
+  acc[W] |= v << C;
+  if (C + D > 32) acc[W + 1] |= v >> ((32 - C) & 31);
+}
+
+template <int D, int K>
+struct RowUnroll {
+  static __device__ __forceinline__ void run(uint32_t (&acc)[(3 * D * D + 31) / 32], const uint32_t* ro,
+                                             const uint32_t* ra, int WPR, int sh) {
+    constexpr uint32_t MASK = (D == 32) ? 0xFFFFFFFFu : ((1u << D) - 1u);
+    const uint32_t vo = __funnelshift_r(ro[0], ro[1], sh) & MASK;
+    const uint32_t va = __funnelshift_r(ra[0], ra[1], sh) & MASK;
+    insert_bits<D, K * D>(acc, vo);
+    insert_bits<D, D * D + K * D>(acc, va);
+    RowUnroll<D, K + 1>::run(acc, ro + WPR, ra + WPR, WPR, sh);
+  }
+};
+template <int D>
+struct RowUnroll<D, D> {
+  static __device__ __forceinline__ void run(uint32_t (&)[(3 * D * D + 31) / 32], const uint32_t*, const uint32_t*,
+                                             int, int) {}
+};
+
+template <int D>
+__device__ __forceinline__ void agent_bits_static(const uint32_t* s_obst, const uint32_t* s_abits, uint32_t* stage,
+                                                  int WPR, int x, int y, uint32_t bitpos, bool word_aligned) {
+  constexpr int R = D / 2;
+  constexpr int NW = (3 * D * D + 31) / 32;
+  uint32_t acc[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) acc[i] = 0u;
+  const int y0 = y - R;
+  const int w = y0 >> 5, sh = y0 & 31;
+  const int rowoff = (x - R) * WPR + w;
+  RowUnroll<D, 0>::run(acc, s_obst + rowoff, s_abits + rowoff, WPR, sh);
+  const uint32_t wbase = bitpos >> 5;
+  if (word_aligned) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) stage[wbase + i] = acc[i];
+  } else {
+    const uint32_t s = bitpos & 31u;
+    uint32_t prev = 0u;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const uint32_t out = __funnelshift_l(prev, acc[i], s);
+      if (i == 0 || i >= NW - 1) atomicOr(&stage[wbase + i], out);
+      else stage[wbase + i] = out;
+      prev = acc[i];
+    }
+    const uint32_t tail = __funnelshift_l(prev, 0u, s);
+    if (tail) atomicOr(&stage[wbase + NW], tail);
+  }
+}
+
+// ------------------------------------------------------------------------- //
+// observation generation: batches of agents -> stage bit stream -> HBM
+// ------------------------------------------------------------------------- //
+template <int TEAM, int RT>
 __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int tid, int bar_id, const uint32_t* s_obst,
                                                   const uint32_t* s_abits, uint32_t* stage, const uint32_t* s_npos,
                                                   const uint32_t* s_tgt) {
-  const int r = p.r, D = p.D, WPR = p.WPR;
-  const int bpa = p.bits_per_agent, sbpa = p.stage_bpa;
+  const int r = (RT > 0) ? RT : p.r;
+  const int D = 2 * r + 1;
+  const int bpa = 3 * D * D, sbpa = p.stage_bpa;
+  const bool word_aligned = (sbpa & 31) == 0;
   for (int g0 = 0; g0 < p.A; g0 += p.batch_agents) {
     const int gcount = min(p.batch_agents, p.A - g0);
     const int nbits = gcount * sbpa;
-    const int nwords = (nbits + 31) / 32 + 1;
-    for (int w = tid; w < nwords; w += TEAM) stage[w] = 0u;
+    const int nvec = ((nbits + 31) / 32 + 1 + 3) >> 2;  // stage is padded to a multiple of 16 bytes
+    uint4* stage4 = reinterpret_cast<uint4*>(stage);
+    for (int w = tid; w < nvec; w += TEAM) stage4[w] = make_uint4(0u, 0u, 0u, 0u);
     team_sync<TEAM>(bar_id);
-    // ---- per agent: stream channel 0 (obstacles) and 1 (agents) row windows, set the target bit
     for (int s = tid; s < gcount; s += TEAM) {
       const int a = g0 + s;
       const uint32_t pp = s_npos[a];
       const int x = pp & 0xFFFF, y = pp >> 16;
-      uint32_t bitpos = (uint32_t)s * (uint32_t)sbpa;
-      uint32_t widx = bitpos >> 5;
-      uint32_t fill = bitpos & 31u;
-      unsigned long long acc = 0ull;
-      bool first = true;
-      const int y0 = y - r;
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const uint32_t* rows = (ch == 0 ? s_obst : s_abits) + (x - r) * WPR;
-#pragma unroll 1
-        for (int k = 0; k < D; ++k, rows += WPR) {
-          for (int c0 = 0; c0 < D; c0 += 32) {
-            const int nb = min(32, D - c0);
-            const int yy = y0 + c0;
-            const int w = yy >> 5, sh = yy & 31;
-            uint32_t v = __funnelshift_r(rows[w], rows[w + 1], sh);
-            if (nb < 32) v &= (1u << nb) - 1u;
-            acc |= (unsigned long long)v << fill;
-            fill += nb;
-            if (fill >= 32u) {
-              if (first) {
-                atomicOr(&stage[widx], (uint32_t)acc);
-                first = false;
-              } else {
-                stage[widx] = (uint32_t)acc;
-              }
-              widx++;
-              acc >>= 32;
-              fill -= 32u;
-            }
-          }
-        }
-      }
-      if (fill > 0u) atomicOr(&stage[widx], (uint32_t)acc);
-      // channel 2: upstream grid.py :: get_square_target (clamped projection)
+      const uint32_t bitpos = (uint32_t)s * (uint32_t)sbpa;
+      if (RT > 0) agent_bits_static<2 * (RT > 0 ? RT : 1) + 1>(s_obst, s_abits, stage, p.WPR, x, y, bitpos, word_aligned);
+      else agent_bits_generic(p, s_obst, s_abits, stage, x, y, bitpos);
+      // channel 2: upstream grid.py :: get_square_target (clamped projection of the goal)
       const uint32_t tt = s_tgt[a];
       int dx = x - (int)(tt & 0xFFFF), dy = y - (int)(tt >> 16);
       dx = max(-r, min(r, dx));
       dy = max(-r, min(r, dy));
-      const uint32_t tb = (uint32_t)s * (uint32_t)sbpa + 2u * D * D + (uint32_t)(r - dx) * D + (uint32_t)(r - dy);
+      const uint32_t tb = bitpos + 2u * D * D + (uint32_t)(r - dx) * D + (uint32_t)(r - dy);
       atomicOr(&stage[tb >> 5], 1u << (tb & 31u));
     }
     team_sync<TEAM>(bar_id);
@@ -251,16 +321,31 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int 
       head = min(head, nbytes);
       const int chunks = (nbytes - head) >> 4;
       uint4* out16 = reinterpret_cast<uint4*>(out + head);
-      for (int c = tid; c < chunks; c += TEAM) {
-        const uint32_t bit = (uint32_t)head + ((uint32_t)c << 4);
-        const uint32_t w = bit >> 5, sh = bit & 31u;
-        const uint32_t v = __funnelshift_r(stage[w], stage[w + 1], sh);
-        uint4 o;
-        o.x = expand4(v & 15u);
-        o.y = expand4((v >> 4) & 15u);
-        o.z = expand4((v >> 8) & 15u);
-        o.w = expand4((v >> 12) & 15u);
-        __stcs(out16 + c, o);
+      if (head == 0) {
+        // aligned fast path: chunk c <- 16 stage bits at halfword c
+        const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
+#pragma unroll 2
+        for (int c = tid; c < chunks; c += TEAM) {
+          const uint32_t v = st16[c];
+          uint4 o;
+          o.x = expand4(v & 15u);
+          o.y = expand4((v >> 4) & 15u);
+          o.z = expand4((v >> 8) & 15u);
+          o.w = expand4(v >> 12);
+          __stcs(out16 + c, o);
+        }
+      } else {
+        for (int c = tid; c < chunks; c += TEAM) {
+          const uint32_t bit = (uint32_t)head + ((uint32_t)c << 4);
+          const uint32_t w = bit >> 5, sh = bit & 31u;
+          const uint32_t v = __funnelshift_r(stage[w], stage[w + 1], sh);
+          uint4 o;
+          o.x = expand4(v & 15u);
+          o.y = expand4((v >> 4) & 15u);
+          o.z = expand4((v >> 8) & 15u);
+          o.w = expand4((v >> 12) & 15u);
+          __stcs(out16 + c, o);
+        }
       }
       const int tail0 = head + (chunks << 4);
       for (int b = tid; b < head + (nbytes - tail0); b += TEAM) {
@@ -275,8 +360,19 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int 
 // ------------------------------------------------------------------------- //
 // the fused step kernel
 // ------------------------------------------------------------------------- //
-template <int TEAM, int COLL, int OP>
-__global__ void __launch_bounds__(1024) pgm_step_kernel(const StepArgs p) {
+// Agent state word (uint2 per agent): .x = x | active << 15 | y << 16 (padded
+// coordinates), .y = target x | y << 16.
+__device__ __forceinline__ uint32_t st_pos(uint32_t w) { return w & 0xFFFF7FFFu; }
+__device__ __forceinline__ uint32_t st_active(uint32_t w) { return (w >> 15) & 1u; }
+
+// Programmatic dependent launch (PTX griddepcontrol): the launch latency and the
+// prologue of step t+1 (shared memory fills, obstacle bulk copy) hide under step t.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int TEAM, int COLL, int OP, int RT>
+__global__ void __launch_bounds__((TEAM < 128 ? 128 : TEAM), (TEAM < 128 ? 8 : (TEAM <= 512 ? 1024 / TEAM : 1)))
+    pgm_step_kernel(const StepArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int team = threadIdx.x / TEAM;
   const int tid = threadIdx.x % TEAM;
@@ -301,7 +397,11 @@ __global__ void __launch_bounds__(1024) pgm_step_kernel(const StepArgs p) {
   const int ONTGT = p.on_target;
   const long long ia = (long long)n * A;
 
-  // ---- phase 0: obstacle map by bulk copy; state into shared memory -------
+  // Let the next launch in the stream be scheduled as soon as SM resources free up: its
+  // prologue (phase 0a) overlaps this grid's tail; its griddepcontrol.wait still waits for
+  // this grid to complete and flush, so there is no cross-step race on any buffer.
+  pdl_trigger();
+  // ---- phase 0a (independent of the previous step): obstacle map by bulk copy, fills
   if (tid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
@@ -311,36 +411,59 @@ __global__ void __launch_bounds__(1024) pgm_step_kernel(const StepArgs p) {
     mbar_expect_tx(s_bar, bytes);
     bulk_g2s(s_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
   }
-  const int grid_words = p.PH * WPR + 1;
-  for (int w = tid; w < grid_words; w += TEAM) s_abits[w] = 0u;
-  if (OP == OP_STEP) {
-    const int occ_words = (p.PH * PW + 1) >> 1;
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(s_occ);
-    for (int w = tid; w < occ_words; w += TEAM) o32[w] = 0xFFFFFFFFu;
-  }
-  for (int a = tid; a < A; a += TEAM) {
-    uint32_t pp, tt;
-    uint8_t fl;
-    if (OP == OP_RESET) {
-      pp = p.pos0[ia + a];
-      tt = p.tgt0[ia + a];
-      fl = 1;
-    } else {
-      pp = p.pos[ia + a];
-      tt = p.tgt[ia + a];
-      fl = p.active[ia + a] & 1u;
-    }
-    s_pos[a] = pp;
-    s_npos[a] = pp;
-    s_tgt[a] = tt;
-    s_flag[a] = fl;
+  {
+    // both regions are padded to multiples of 16 bytes by the host-side layout
+    const int abits_vec = (p.PH * WPR + 1 + 3) >> 2;
+    uint4* a4 = reinterpret_cast<uint4*>(s_abits);
+    for (int w = tid; w < abits_vec; w += TEAM) a4[w] = make_uint4(0u, 0u, 0u, 0u);
     if (OP == OP_STEP) {
-      uint32_t act = p.actions[(ia + a) * p.act_itemsize];
-      if (act > 4u) {
+      const int occ_vec = (p.PH * PW * 2 + 4 + 15) >> 4;
+      uint4* o4 = reinterpret_cast<uint4*>(s_occ);
+      for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+  }
+  // ---- phase 0b: mutable state of this instance (two agents per thread in flight)
+  pdl_wait();
+  int step_idx = 0;
+  int m_acc0 = 0, m_acc1 = 0, m_acc2 = 0;
+  if (OP == OP_STEP) {
+    step_idx = p.elapsed[n];
+    const int4 m = *reinterpret_cast<const int4*>(p.metric_acc + 4 * (long long)n);
+    m_acc0 = m.x;
+    m_acc1 = m.y;
+    m_acc2 = m.z;
+  }
+  const uint2* src = (OP == OP_RESET) ? p.state0 : p.state;
+  for (int a0 = tid; a0 < A; a0 += 2 * TEAM) {
+    const int a1 = a0 + TEAM;
+    const bool has1 = a1 < A;
+    uint2 w0 = src[ia + a0];
+    uint2 w1 = has1 ? src[ia + a1] : make_uint2(0u, 0u);
+    uint32_t act0 = 0u, act1 = 0u;
+    if (OP == OP_STEP) {
+      act0 = p.actions[(ia + a0) * p.act_itemsize];
+      if (has1) act1 = p.actions[(ia + a1) * p.act_itemsize];
+      if (act0 > 4u || act1 > 4u) {
         atomicOr(p.err_flag, 1);
-        act = 0u;
+        if (act0 > 4u) act0 = 0u;
+        if (act1 > 4u) act1 = 0u;
       }
-      s_act[a] = (uint8_t)act;
+    }
+    if (OP == OP_RESET) {
+      w0.x |= 0x8000u;
+      w1.x |= 0x8000u;
+    }
+    s_pos[a0] = st_pos(w0.x);
+    s_npos[a0] = st_pos(w0.x);
+    s_tgt[a0] = w0.y;
+    s_flag[a0] = (uint8_t)st_active(w0.x);
+    if (OP == OP_STEP) s_act[a0] = (uint8_t)act0;
+    if (has1) {
+      s_pos[a1] = st_pos(w1.x);
+      s_npos[a1] = st_pos(w1.x);
+      s_tgt[a1] = w1.y;
+      s_flag[a1] = (uint8_t)st_active(w1.x);
+      if (OP == OP_STEP) s_act[a1] = (uint8_t)act1;
     }
   }
   team_sync<TEAM>(bar_id);
@@ -453,19 +576,16 @@ __global__ void __launch_bounds__(1024) pgm_step_kernel(const StepArgs p) {
     }
     c_on = __reduce_add_sync(0xffffffffu, c_on);
     c_was = __reduce_add_sync(0xffffffffu, c_was);
-    if ((threadIdx.x & 31) == 0) {
-      if (TEAM == 32) {
-        s_cnt[0] = c_on;
-        s_cnt[1] = c_was;
-      } else {
+    if (TEAM > 32) {
+      if ((threadIdx.x & 31) == 0) {
         atomicAdd(&s_cnt[0], c_on);
         atomicAdd(&s_cnt[1], c_was);
       }
+      team_sync<TEAM>(bar_id);
+      c_on = s_cnt[0];
+      c_was = s_cnt[1];
     }
-    team_sync<TEAM>(bar_id);  // also: every read of occ is done -> stage may reuse it
-    c_on = s_cnt[0];
-    c_was = s_cnt[1];
-    const int step_idx = p.elapsed[n];
+    // (all reads of occ are done: the barrier after pointer jumping; stage may reuse it)
     const bool trunc = (step_idx + 1 >= p.max_steps);
     const bool solved = (c_was == A);
     const bool all_term = (ONTGT == 2) ? false : (c_on == A);
@@ -502,60 +622,48 @@ __global__ void __launch_bounds__(1024) pgm_step_kernel(const StepArgs p) {
       p.was_on_goal[ia + a] = (uint8_t)was;
       uint32_t pp = s_npos[a];
       if (do_reset) {
-        pp = p.pos0[ia + a];
-        tt = p.tgt0[ia + a];
+        const uint2 w = p.state0[ia + a];
+        pp = st_pos(w.x);
+        tt = w.y;
         nfl = 1u;
         if (ONTGT == 2) p.rng[ia + a] = p.rng0[ia + a];
       }
       s_npos[a] = pp;
       s_tgt[a] = tt;
       s_flag[a] = (uint8_t)nfl;
-      p.pos[ia + a] = pp;
-      p.tgt[ia + a] = tt;
-      p.active[ia + a] = (uint8_t)nfl;
+      p.state[ia + a] = make_uint2(pp | (nfl << 15), tt);
     }
     if (tid == 0) {
       p.elapsed[n] = do_reset ? 0 : step_idx + 1;
       p.episode_done[n] = done ? 1 : 0;
       // raw counters of upstream wrappers/metrics.py
-      int32_t* acc = p.metric_acc + 4 * (long long)n;
-      const int mstep = acc[2];
-      const int solved_sum = acc[0] + c_was;
-      const int time_sum = acc[1] + c_was * mstep;
+      const int mstep = m_acc2;
+      const int solved_sum = m_acc0 + c_was;
+      const int time_sum = m_acc1 + c_was * mstep;
+      int4* acc = reinterpret_cast<int4*>(p.metric_acc + 4 * (long long)n);
       if (done) {
-        int32_t* last = p.metric_last + 4 * (long long)n;
-        last[0] = solved_sum;
-        last[1] = time_sum + (A - solved_sum) * mstep;
-        last[2] = mstep + 1;
-        last[3] = c_was;
-        acc[0] = 0;
-        acc[1] = 0;
-        acc[2] = 0;
+        int4* last = reinterpret_cast<int4*>(p.metric_last + 4 * (long long)n);
+        *last = make_int4(solved_sum, time_sum + (A - solved_sum) * mstep, mstep + 1, c_was);
+        *acc = make_int4(0, 0, 0, 0);
       } else {
-        acc[0] = solved_sum;
-        acc[1] = time_sum;
-        acc[2] = mstep + 1;
+        *acc = make_int4(solved_sum, time_sum, mstep + 1, 0);
       }
     }
   } else {
     if (OP == OP_RESET) {
       for (int a = tid; a < A; a += TEAM) {
-        p.pos[ia + a] = s_pos[a];
-        p.tgt[ia + a] = s_tgt[a];
-        p.active[ia + a] = 1;
+        p.state[ia + a] = make_uint2(s_pos[a] | 0x8000u, s_tgt[a]);
         p.was_on_goal[ia + a] = (s_pos[a] == s_tgt[a]) ? 1 : 0;
         if (ONTGT == 2) p.rng[ia + a] = p.rng0[ia + a];
       }
       if (tid == 0) {
         p.elapsed[n] = 0;
         p.episode_done[n] = 0;
-        int32_t* acc = p.metric_acc + 4 * (long long)n;
-        acc[0] = acc[1] = acc[2] = acc[3] = 0;
+        *reinterpret_cast<int4*>(p.metric_acc + 4 * (long long)n) = make_int4(0, 0, 0, 0);
       }
     }
     mbar_wait(s_bar, 0);
   }
-
   if (p.obs == nullptr) return;
   // ---- phase 4: post-move agent bitmap -------------------------------------
   for (int a = tid; a < A; a += TEAM) {
@@ -567,7 +675,7 @@ __global__ void __launch_bounds__(1024) pgm_step_kernel(const StepArgs p) {
   }
   // (emit_observations starts with stage zeroing + team_sync, which also orders the atomics)
   // ---- phase 5: observations -------------------------------------------------
-  emit_observations<TEAM>(p, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
+  emit_observations<TEAM, RT>(p, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
 }
 
 }  // namespace pgm

@@ -1,0 +1,45 @@
+"""Quick device-resident timing of the step kernel (development aid, not the bench contract)."""
+import argparse, json, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pogema_b200 import BatchedPogema, GridConfig
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=4096)
+ap.add_argument("--size", type=int, default=32)
+ap.add_argument("--agents", type=int, default=64)
+ap.add_argument("--r", type=int, default=5)
+ap.add_argument("--coll", default="priority")
+ap.add_argument("--ot", default="finish")
+ap.add_argument("--team", type=int, default=0)
+ap.add_argument("--steps", type=int, default=128)
+ap.add_argument("--fmt", default="u8")
+ap.add_argument("--noobs", action="store_true")
+a = ap.parse_args()
+gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, max_episode_steps=64,
+                collision_system=a.coll, on_target=a.ot)
+t0 = time.time()
+env = BatchedPogema(gc, num_envs=a.n, auto_reset=True, team_threads=a.team, obs_format=a.fmt)
+t_gen = time.time() - t0
+env.reset()
+acts = [env.sample_actions() for _ in range(16)]
+bufs = [env.new_obs_buffer() for _ in range(4)]
+for i in range(20):
+    env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(a.steps):
+    env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+env.check_errors()
+D = 2 * a.r + 1
+P = a.size + 2 * a.r
+bytes_per = (3 * D * D if a.fmt == "u8" else 4 * ((3 * D * D + 31) // 32)) + 21 + ((P * P + 7) // 8) / a.agents
+if a.noobs:
+    bytes_per = 21 + ((P * P + 7) // 8) / a.agents
+rate = a.n * a.agents / (ms * 1e-3)
+print(json.dumps({"cfg": vars(a), "plan": env.engine.plan(), "gen_s": round(t_gen, 2), "ms_per_step": round(ms, 4),
+                  "agent_steps_per_s": rate, "GBps": rate * bytes_per / 1e9, "frac_6541": rate * bytes_per / 6541.5e9}))
