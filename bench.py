@@ -222,8 +222,26 @@ def run_cuda(args):
     ring = [env.new_obs_buffer() for _ in range(4)]
     stream = torch.cuda.current_stream(dev)
 
-    for i in range(args.warmup):
-        env.step(acts[i % n_act], out=ring[i % 4])
+    # The K timed steps are issued as replays of a CUDA graph holding GRAPH_STEPS consecutive
+    # step launches (launch-bound inner loop -> graph), plus K % GRAPH_STEPS plain launches.
+    GRAPH_STEPS = n_act
+
+    def plain_steps(first, count):
+        for i in range(first, first + count):
+            env.step(acts[i % n_act], out=ring[i % 4])
+
+    plain_steps(0, max(args.warmup, 3))
+    graph = None
+    if not args.no_graph:
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                plain_steps(0, GRAPH_STEPS)
+        stream.wait_stream(side)
+        graph.replay()  # untimed warm-up of the instantiated graph
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -233,12 +251,17 @@ def run_cuda(args):
     launches0 = env.engine.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(args.steps):
-        env.step(acts[i % n_act], out=ring[i % 4])
+    if graph is not None:
+        for _ in range(args.steps // GRAPH_STEPS):
+            graph.replay()
+        plain_steps(0, args.steps % GRAPH_STEPS)
+    else:
+        plain_steps(0, args.steps)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = env.engine.launch_count - launches0
+    # graph replays launch GRAPH_STEPS kernels each without passing through pgm_step
+    launches = (env.engine.launch_count - launches0) + (GRAPH_STEPS * (args.steps // GRAPH_STEPS) if graph is not None else 0)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,6 +313,7 @@ def run_cuda(args):
             "config": {"workload": WORKLOAD_NAME, "instances_per_gpu": N, "agents_per_instance": A,
                        "obs": "uint8 [N,A,3,11,11]", "actions": "uint8 resident in HBM, 16 pre-generated tensors",
                        "l2": "obs written to a ring of 4 buffers (4 x %.0f MB > 126 MB L2)" % (env.engine.obs_bytes / 1e6),
+                       "launch": ("CUDA graph of %d step launches, replayed" % GRAPH_STEPS) if graph is not None else "one pgm_step call per step",
                        "plan": env.engine.plan(), "parallelism": f"instances sharded over {world} GPU(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -314,13 +338,14 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=8192)
+    ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--instances", type=int, default=INSTANCES_PER_GPU, help="instances per GPU")
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graph replays")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

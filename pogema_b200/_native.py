@@ -24,7 +24,7 @@ EXPORTS = [
     "pgm_last_error", "pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_obs_bytes",
     "pgm_obs_instance_stride", "pgm_generate", "pgm_generate_host", "pgm_set_tasks", "pgm_reset", "pgm_observe", "pgm_step",
     "pgm_step_host", "pgm_get_state", "pgm_state_ptr", "pgm_checkpoint_bytes", "pgm_checkpoint_save",
-    "pgm_checkpoint_load", "pgm_check_errors", "pgm_launch_count", "pgm_plan",
+    "pgm_checkpoint_load", "pgm_check_errors", "pgm_launch_count", "pgm_plan", "pgm_set_debug_buffer",
 ]
 
 
@@ -78,6 +78,7 @@ def load():
     lib.pgm_checkpoint_save.argtypes = [vp, vp, i64, vp]
     lib.pgm_checkpoint_load.argtypes = [vp, vp, i64, vp]
     lib.pgm_check_errors.argtypes = [vp, vp]
+    lib.pgm_set_debug_buffer.argtypes = [vp, vp]
     lib.pgm_launch_count.argtypes = [vp]
     lib.pgm_launch_count.restype = i64
     lib.pgm_plan.argtypes = [vp, C.POINTER(i32), i32]

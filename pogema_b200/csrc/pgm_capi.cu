@@ -74,6 +74,7 @@ struct pgm_engine {
   int32_t *d_cstart = nullptr, *d_csize = nullptr;
   uint32_t* d_cells = nullptr;
   int* d_err = nullptr;
+  long long* d_debug = nullptr;  // caller-owned, see pgm_set_debug_buffer
   // step_host scratch
   uint8_t *d_act_h = nullptr, *d_obs_h = nullptr, *d_term_h = nullptr, *d_trunc_h = nullptr;
   float* d_rew_h = nullptr;
@@ -142,7 +143,12 @@ int compute_plan(pgm_engine* e) {
   L.team_smem = round_up(off, 16);
   if (L.team_smem > smem_max)
     return fail(PGM_ERR_UNSUPPORTED, "instance needs %d bytes of shared memory (max %d)", L.team_smem, smem_max);
-  int tpc = std::max(1, 128 / team);
+  // teams per CTA: about half of the teams an SM hosts (two CTAs per SM), fewer launches of larger CTAs
+  const int per_sm_teams = (c.num_envs + e->sm_count - 1) / e->sm_count;
+  int tpc = std::max(1, std::min(16, (per_sm_teams + 1) / 2));
+  tpc = std::max(tpc, std::min(4, 128 / team));
+  if (const char* v = getenv("PGM_TPC")) tpc = std::max(1, atoi(v));  // tuning knob
+  tpc = std::min(tpc, 1024 / team);
   while (tpc > 1 && tpc * L.team_smem > smem_max) tpc--;
   if (team > 32) tpc = std::min(tpc, 15);
   e->tpc = tpc;
@@ -212,6 +218,7 @@ StepArgs make_args(pgm_engine* e) {
   a.terminated = nullptr;
   a.truncated = nullptr;
   a.err_flag = e->d_err;
+  a.debug = e->d_debug;
   return a;
 }
 
@@ -702,6 +709,12 @@ int pgm_checkpoint_load(pgm_engine* e, const void* src, int64_t src_bytes, void*
     o += p.bytes;
   }
   CUDA_TRY(cudaStreamSynchronize(s));
+  return PGM_OK;
+}
+
+int pgm_set_debug_buffer(pgm_engine* e, void* dev_ptr) {
+  if (!e) return fail(PGM_ERR_INVALID, "null engine");
+  e->d_debug = (long long*)dev_ptr;
   return PGM_OK;
 }
 

@@ -70,6 +70,7 @@ struct StepArgs {
   uint8_t* terminated;
   uint8_t* truncated;
   int* err_flag;
+  long long* debug;     // optional [N][16] clock64 stamps at phase boundaries (tools/phase_timeline.py)
   // shared memory layout, byte offsets inside a team slice
   int off_obst, off_abits, off_occ, off_pos, off_tgt, off_npos, off_link, off_act, off_flag, off_misc;
   int team_smem;
@@ -278,6 +279,11 @@ __device__ __forceinline__ void agent_bits_static(const uint32_t* s_obst, const 
 // ------------------------------------------------------------------------- //
 // observation generation: batches of agents -> stage bit stream -> HBM
 // ------------------------------------------------------------------------- //
+#define PGM_STAMP(k)                                                        \
+  do {                                                                      \
+    if (p.debug != nullptr && tid == 0) p.debug[(long long)n * 16 + (k)] = clock64(); \
+  } while (0)
+
 template <int TEAM, int RT>
 __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int tid, int bar_id, const uint32_t* s_obst,
                                                   const uint32_t* s_abits, uint32_t* stage, const uint32_t* s_npos,
@@ -293,6 +299,7 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int 
     uint4* stage4 = reinterpret_cast<uint4*>(stage);
     for (int w = tid; w < nvec; w += TEAM) stage4[w] = make_uint4(0u, 0u, 0u, 0u);
     team_sync<TEAM>(bar_id);
+    PGM_STAMP(6);
     for (int s = tid; s < gcount; s += TEAM) {
       const int a = g0 + s;
       const uint32_t pp = s_npos[a];
@@ -309,6 +316,7 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int 
       atomicOr(&stage[tb >> 5], 1u << (tb & 31u));
     }
     team_sync<TEAM>(bar_id);
+    PGM_STAMP(7);
     // ---- write out
     if (p.obs_format == 1) {
       const int wpa = sbpa >> 5;
@@ -324,7 +332,7 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int 
       if (head == 0) {
         // aligned fast path: chunk c <- 16 stage bits at halfword c
         const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
-#pragma unroll 2
+#pragma unroll 4
         for (int c = tid; c < chunks; c += TEAM) {
           const uint32_t v = st16[c];
           uint4 o;
@@ -355,6 +363,7 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int 
     }
     if (g0 + p.batch_agents < p.A) team_sync<TEAM>(bar_id);
   }
+  PGM_STAMP(8);
 }
 
 // ------------------------------------------------------------------------- //
@@ -371,7 +380,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <int TEAM, int COLL, int OP, int RT>
-__global__ void __launch_bounds__((TEAM < 128 ? 128 : TEAM), (TEAM < 128 ? 8 : (TEAM <= 512 ? 1024 / TEAM : 1)))
+__global__ void __launch_bounds__((TEAM < 128 ? 1024 : TEAM), (TEAM < 128 ? 1 : (TEAM <= 512 ? 1024 / TEAM : 1)))
     pgm_step_kernel(const StepArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int team = threadIdx.x / TEAM;
@@ -401,6 +410,7 @@ __global__ void __launch_bounds__((TEAM < 128 ? 128 : TEAM), (TEAM < 128 ? 8 : (
   // prologue (phase 0a) overlaps this grid's tail; its griddepcontrol.wait still waits for
   // this grid to complete and flush, so there is no cross-step race on any buffer.
   pdl_trigger();
+  PGM_STAMP(0);
   // ---- phase 0a (independent of the previous step): obstacle map by bulk copy, fills
   if (tid == 0) {
     mbar_init(s_bar, 1);
@@ -423,7 +433,9 @@ __global__ void __launch_bounds__((TEAM < 128 ? 128 : TEAM), (TEAM < 128 ? 8 : (
     }
   }
   // ---- phase 0b: mutable state of this instance (two agents per thread in flight)
+  PGM_STAMP(1);
   pdl_wait();
+  PGM_STAMP(2);
   int step_idx = 0;
   int m_acc0 = 0, m_acc1 = 0, m_acc2 = 0;
   if (OP == OP_STEP) {
@@ -478,6 +490,7 @@ __global__ void __launch_bounds__((TEAM < 128 ? 128 : TEAM), (TEAM < 128 ? 8 : (
     }
     team_sync<TEAM>(bar_id);
     mbar_wait(s_bar, 0);
+    PGM_STAMP(3);
 
     // ---- phase 2: move resolution -----------------------------------------
     if (COLL == 2) {
@@ -556,6 +569,7 @@ __global__ void __launch_bounds__((TEAM < 128 ? 128 : TEAM), (TEAM < 128 ? 8 : (
       }
     }
     team_sync<TEAM>(bar_id);
+    PGM_STAMP(4);
 
     // ---- phase 3: apply moves, on_target bookkeeping, time limit -----------
     int c_on = 0, c_was = 0;
@@ -664,6 +678,7 @@ __global__ void __launch_bounds__((TEAM < 128 ? 128 : TEAM), (TEAM < 128 ? 8 : (
     }
     mbar_wait(s_bar, 0);
   }
+  PGM_STAMP(5);
   if (p.obs == nullptr) return;
   // ---- phase 4: post-move agent bitmap -------------------------------------
   for (int a = tid; a < A; a += TEAM) {

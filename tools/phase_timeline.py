@@ -1,0 +1,34 @@
+"""Per-phase cycle timeline of the step kernel (clock64 stamps, see pgm_set_debug_buffer)."""
+import argparse, sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pogema_b200 import BatchedPogema, GridConfig
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=4096); ap.add_argument("--agents", type=int, default=64)
+ap.add_argument("--size", type=int, default=32); ap.add_argument("--r", type=int, default=5)
+ap.add_argument("--coll", default="priority"); ap.add_argument("--ot", default="finish")
+ap.add_argument("--fmt", default="u8")
+a = ap.parse_args()
+gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, collision_system=a.coll, on_target=a.ot)
+env = BatchedPogema(gc, num_envs=a.n, auto_reset=True, obs_format=a.fmt)
+env.reset()
+acts = [env.sample_actions() for _ in range(8)]
+bufs = [env.new_obs_buffer() for _ in range(4)]
+for i in range(20): env.step(acts[i % 8], out=bufs[i % 4])
+dbg = torch.zeros((a.n, 16), dtype=torch.int64, device="cuda")
+env.engine.lib.pgm_set_debug_buffer(env.engine.handle, C.c_void_p(dbg.data_ptr()))
+torch.cuda.synchronize()
+for i in range(3): env.step(acts[i % 8], out=bufs[i % 4])
+torch.cuda.synchronize()
+env.engine.lib.pgm_set_debug_buffer(env.engine.handle, None)
+d = dbg.cpu().numpy().astype(np.float64)
+names = ["start", "prologue", "pdl_wait", "load+occ+mbar", "resolve", "bookkeeping", "abits+zero", "gen", "expand+store"]
+# clock64 is per-SM: only differences within an instance are meaningful
+print("plan", env.engine.plan())
+prev = d[:, 0]
+for k in range(1, 9):
+    dt = d[:, k] - d[:, k - 1]
+    print("%-16s mean %8.0f  p50 %8.0f  p95 %8.0f  max %8.0f cycles" % (names[k], dt.mean(), np.percentile(dt, 50), np.percentile(dt, 95), dt.max()))
+tot = d[:, 8] - d[:, 0]
+print("%-16s mean %8.0f  p50 %8.0f  p95 %8.0f  max %8.0f cycles" % ("total", tot.mean(), np.percentile(tot, 50), np.percentile(tot, 95), tot.max()))

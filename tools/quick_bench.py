@@ -15,6 +15,7 @@ ap.add_argument("--team", type=int, default=0)
 ap.add_argument("--steps", type=int, default=128)
 ap.add_argument("--fmt", default="u8")
 ap.add_argument("--noobs", action="store_true")
+ap.add_argument("--graph", type=int, default=0)
 a = ap.parse_args()
 gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, max_episode_steps=64,
                 collision_system=a.coll, on_target=a.ot)
@@ -28,10 +29,26 @@ for i in range(20):
     env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for i in range(a.steps):
-    env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
-e1.record()
+if a.graph:
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for i in range(a.graph):
+                env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
+    torch.cuda.synchronize()
+    g.replay(); torch.cuda.synchronize()
+    reps = max(1, a.steps // a.graph)
+    a.steps = reps * a.graph
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+else:
+    e0.record()
+    for i in range(a.steps):
+        env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
+    e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 env.check_errors()
