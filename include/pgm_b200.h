@@ -177,6 +177,9 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
                   float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host,
                   void* stream);
 
+/* upstream Pogema._obs with a HOST destination buffer (copies device->host, synchronises). */
+int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream);
+
 /* State access (debugging, env.grid accessors, checkpoint/resume). */
 int pgm_get_state(pgm_engine* e, int32_t what, void* dst_host, int64_t dst_bytes, void* stream);
 void* pgm_state_ptr(pgm_engine* e, int32_t what); /* device pointer of the raw array, or NULL */

@@ -581,6 +581,19 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
   return PGM_OK;
 }
 
+int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream) {
+  if (!e || !obs_host) return fail(PGM_ERR_INVALID, "null argument");
+  DeviceGuard guard(e->cfg.device);
+  int rc = ensure_host_scratch(e, 1);
+  if (rc != PGM_OK) return rc;
+  rc = pgm_observe(e, e->d_obs_h, stream);
+  if (rc != PGM_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return PGM_OK;
+}
+
 int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, void* stream) {
   if (!e || !dst) return fail(PGM_ERR_INVALID, "null argument");
   DeviceGuard guard(e->cfg.device);

@@ -73,9 +73,12 @@ class Engine:
             count = len(seeds)
             m = gc.map_array()
             if m is None:
-                # explicit agents on a generated map: obstacles still come from the seed
-                raise NotImplementedError("agents_xy/targets_xy without an explicit map is not supported")
-            obst = np.ascontiguousarray(np.broadcast_to(m, (count,) + m.shape))
+                # explicit agents on a generated map: the obstacles still come from the seed through the
+                # reference's own RNG call (upstream generator.py :: generate_obstacles), drawn on the host
+                obst = np.stack([np.random.default_rng(int(s)).binomial(1, gc.density, (gc.size, gc.size))
+                                 for s in seeds]).astype(np.uint8)
+            else:
+                obst = np.ascontiguousarray(np.broadcast_to(m, (count,) + m.shape))
             axy = np.ascontiguousarray(np.broadcast_to(np.asarray(gc.agents_xy, dtype=np.int32),
                                                        (count, self.num_agents, 2)))
             txy = np.ascontiguousarray(np.broadcast_to(np.asarray(gc.targets_xy, dtype=np.int32),
@@ -128,13 +131,10 @@ class Engine:
                                          _ptr(terminated), _ptr(truncated), C.c_void_p(stream)))
 
     def observe_host(self, stream: int = 0) -> np.ndarray:
-        """Observation of the current state as a host array (allocates device scratch via cudart)."""
-        import torch  # only for a device scratch buffer
-        with torch.cuda.device(self.device):
-            buf = torch.empty(self.obs_bytes, dtype=torch.uint8, device=f"cuda:{self.device}")
-            self.observe(buf.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            host = buf.cpu().numpy()
-        return host.view(self.obs_dtype()).reshape(self.obs_shape())
+        """Observation of the current state as a host array (pgm_observe_host)."""
+        out = np.empty(self.obs_shape(), dtype=self.obs_dtype())
+        nat.check(self.lib.pgm_observe_host(self.handle, _ptr(out), C.c_void_p(stream)))
+        return out
 
     # -- state ----------------------------------------------------------------------- #
     def get_state(self, what: int, stream: int = 0) -> np.ndarray:

@@ -1,0 +1,313 @@
+"""List based single-instance environments - drop-in for upstream
+``pogema_v0(grid_config)`` (upstream integrations/make_pogema.py :: make_pogema,
+envs.py :: Pogema / PogemaLifeLong / PogemaCoopFinish, wrappers/multi_time_limit.py,
+wrappers/metrics.py).  One ``Engine`` with a single instance does all the work:
+every ``step`` is one launch of the fused sm_100a kernel through the C-ABI host
+buffer call (``pgm_step_host``); nothing is computed on the CPU except turning
+arrays into the Python lists the upstream API returns."""
+from __future__ import annotations
+
+import os
+from copy import deepcopy
+from typing import Optional
+
+import numpy as np
+
+from . import _native as nat
+from .engine import Engine
+from .grid_config import GridConfig
+
+try:  # gymnasium is optional (absent in this image): fall back to minimal space shims
+    import gymnasium
+    from gymnasium.spaces import Box, Discrete
+    _Base = gymnasium.Env
+except Exception:  # pragma: no cover - exercised when gymnasium is missing
+    gymnasium = None
+
+    class Discrete:
+        def __init__(self, n):
+            self.n = int(n)
+            self.shape = ()
+            self.dtype = np.int64
+
+        def sample(self):
+            return int(np.random.randint(self.n))
+
+        def contains(self, x):
+            return 0 <= int(x) < self.n
+
+    class Box:
+        def __init__(self, low, high, shape, dtype=np.float32):
+            self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+        def contains(self, x):
+            return tuple(np.shape(x)) == self.shape
+
+    _Base = object
+
+
+class ActionsSampler:
+    """upstream envs.py :: ActionsSampler"""
+
+    def __init__(self, num_actions, seed=42):
+        self._num_actions = num_actions
+        self._rnd = None
+        self.update_seed(seed)
+
+    def update_seed(self, seed=None):
+        self._rnd = np.random.default_rng(seed)
+
+    def sample_actions(self, dim=1):
+        return self._rnd.integers(self._num_actions, size=dim)
+
+
+class GridView:
+    """Read-only stand-in for upstream ``grid.py :: Grid`` built from device state
+    (``env.grid.get_agents_xy()`` etc. keep working)."""
+
+    def __init__(self, env):
+        self._env = env
+        self.config = env.grid_config
+
+    def _state(self, what):
+        return self._env._engine.get_state(what)[0]
+
+    @property
+    def obstacles(self):
+        """Padded obstacle array (float, like upstream after add_artificial_border)."""
+        gc = self.config
+        r = gc.obs_radius
+        inner = self._state(nat.STATE_OBSTACLES).astype(np.float64)
+        h, w = inner.shape
+        full = np.zeros((h + 2 * r, w + 2 * r))
+        full[r - 1, r - 1:w + r + 1] = gc.OBSTACLE
+        full[r - 1:h + r + 1, r - 1] = gc.OBSTACLE
+        full[h + r, r - 1:w + r + 1] = gc.OBSTACLE
+        full[r - 1:h + r + 1, w + r] = gc.OBSTACLE
+        full[r:h + r, r:w + r] = inner
+        return full
+
+    @property
+    def positions_xy(self):
+        r = self.config.obs_radius
+        return [(int(x) + r, int(y) + r) for x, y in self._state(nat.STATE_POSITIONS)]
+
+    @property
+    def finishes_xy(self):
+        r = self.config.obs_radius
+        return [(int(x) + r, int(y) + r) for x, y in self._state(nat.STATE_TARGETS)]
+
+    @property
+    def is_active(self):
+        return {i: bool(v) for i, v in enumerate(self._state(nat.STATE_ACTIVE))}
+
+    @property
+    def positions(self):
+        occ = np.zeros_like(self.obstacles)
+        for (x, y), act in zip(self.positions_xy, self.is_active.values()):
+            if act:
+                occ[x, y] = self.config.OBSTACLE
+        return occ
+
+    def get_obstacles(self, ignore_borders=False):
+        if ignore_borders:
+            return self._state(nat.STATE_OBSTACLES).astype(np.float64)
+        return self.obstacles
+
+    def _prepare(self, what, only_active, ignore_borders):
+        r = 0 if ignore_borders else self.config.obs_radius
+        pts = [[int(x) + r, int(y) + r] for x, y in self._state(what)]
+        if only_active:
+            act = self._state(nat.STATE_ACTIVE)
+            pts = [p for p, a in zip(pts, act) if a]
+        return pts
+
+    def get_agents_xy(self, only_active=False, ignore_borders=False):
+        return self._prepare(nat.STATE_POSITIONS, only_active, ignore_borders)
+
+    def get_targets_xy(self, only_active=False, ignore_borders=False):
+        return self._prepare(nat.STATE_TARGETS, only_active, ignore_borders)
+
+    def get_agents_xy_relative(self):
+        return self._relative(self.get_agents_xy())
+
+    def get_targets_xy_relative(self):
+        return self._relative(self.get_targets_xy())
+
+    def _relative(self, pts):
+        r = self.config.obs_radius
+        start = [[x + r, y + r] for x, y in self._env._initial_xy]
+        return [[x - sx, y - sy] for (x, y), (sx, sy) in zip(pts, start)]
+
+    def on_goal(self, agent_id):
+        return self.positions_xy[agent_id] == self.finishes_xy[agent_id]
+
+    def is_active_agent(self, agent_id):
+        return self.is_active[agent_id]
+
+    def get_state(self, ignore_borders=False, as_dict=False):
+        obstacles = self.get_obstacles(ignore_borders)
+        agents_xy = self.get_agents_xy(ignore_borders=ignore_borders)
+        targets_xy = self.get_targets_xy(ignore_borders=ignore_borders)
+        active = [self.is_active[i] for i in range(len(agents_xy))]
+        if as_dict:
+            return {"obstacles": obstacles, "agents_xy": agents_xy, "targets_xy": targets_xy, "active": active}
+        return obstacles, agents_xy, targets_xy, active
+
+
+class Pogema(_Base):
+    """One POGEMA instance with the upstream list based API.  ``on_target``
+    selects the upstream class it stands for (finish -> Pogema, restart ->
+    PogemaLifeLong, nothing -> PogemaCoopFinish); the time limit
+    (MultiTimeLimit) and the metric wrappers are part of the same object."""
+
+    metadata = {"render_modes": ["ansi"]}
+
+    def __init__(self, grid_config: Optional[GridConfig] = None, device: int = 0, **kwargs):
+        if grid_config is None:
+            grid_config = GridConfig(**kwargs)
+        elif isinstance(grid_config, dict):
+            grid_config = GridConfig(**grid_config)
+        if grid_config.observation_type != 'default':
+            raise NotImplementedError("observation_type must be 'default' (POMAPF/MAPF dict observations are not built)")
+        self.grid_config = grid_config
+        self._device = int(device)
+        self._engine = None
+        self._engine_key = None
+        self.grid = None
+        self.was_on_goal = None
+        self._initial_xy = None
+        full = grid_config.obs_radius * 2 + 1
+        self.action_space = Discrete(len(grid_config.MOVES))
+        self.observation_space = Box(0.0, 1.0, shape=(3, full, full), dtype=np.float32)
+        self._multi_action_sampler = ActionsSampler(self.action_space.n, seed=grid_config.seed)
+        self._elapsed_steps = None
+
+    # -- helpers --------------------------------------------------------- #
+    def _ensure_engine(self):
+        gc = self.grid_config
+        key = (gc.num_agents, gc.map_shape(), gc.obs_radius, gc.max_episode_steps, gc.collision_system, gc.on_target)
+        if self._engine is None or key != self._engine_key:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(gc, 1, device=self._device, auto_reset=False)
+            self._engine_key = key
+            n, a = 1, gc.num_agents
+            self._h_obs = np.empty(self._engine.obs_shape(), dtype=np.uint8)
+            self._h_rew = np.empty((n, a), dtype=np.float32)
+            self._h_term = np.empty((n, a), dtype=np.uint8)
+            self._h_trunc = np.empty((n, a), dtype=np.uint8)
+        self._engine.grid_config = gc
+
+    def _obs_list(self, obs_u8):
+        return [obs_u8[0, i].astype(np.float32) for i in range(self.grid_config.num_agents)]
+
+    def _get_infos(self):
+        active = self._engine.get_state(nat.STATE_ACTIVE)[0]
+        return [dict(is_active=bool(active[i])) for i in range(self.grid_config.num_agents)]
+
+    # -- gymnasium style API ------------------------------------------------ #
+    def reset(self, seed: Optional[int] = None, return_info: bool = True, options: Optional[dict] = None):
+        if seed is not None:
+            self.grid_config.seed = seed
+        self._ensure_engine()
+        task_seed = self.grid_config.seed
+        if task_seed is None:  # upstream: default_rng(None) - fresh OS entropy every reset
+            task_seed = int.from_bytes(os.urandom(7), "little")
+        self._engine.generate([task_seed])
+        obs = self._engine.observe_host()
+        self._multi_action_sampler.update_seed(self.grid_config.seed)
+        self._initial_xy = self._engine.get_state(nat.STATE_POSITIONS)[0].tolist()
+        self.grid = GridView(self)
+        pos = self._engine.get_state(nat.STATE_POSITIONS)[0]
+        tgt = self._engine.get_state(nat.STATE_TARGETS)[0]
+        self.was_on_goal = [bool((pos[i] == tgt[i]).all()) for i in range(self.grid_config.num_agents)]
+        self._elapsed_steps = 0
+        return self._obs_list(obs), self._get_infos()
+
+    def step(self, action):
+        assert len(action) == self.grid_config.num_agents
+        act = np.asarray(action)
+        if act.size and (act.min() < 0 or act.max() >= self.action_space.n):
+            raise IndexError("action out of range [0, %d)" % self.action_space.n)
+        act = np.ascontiguousarray(act.astype(np.uint8).reshape(1, -1))
+        self._engine.step_host(act, self._h_obs, self._h_rew, self._h_term, self._h_trunc)
+        self._elapsed_steps += 1
+        n = self.grid_config.num_agents
+        rewards = [float(self._h_rew[0, i]) for i in range(n)]
+        terminated = [bool(self._h_term[0, i]) for i in range(n)]
+        truncated = [bool(self._h_trunc[0, i]) for i in range(n)]
+        self.was_on_goal = [bool(v) for v in self._engine.get_state(nat.STATE_WAS_ON_GOAL)[0]]
+        infos = self._get_infos()
+        if all(truncated) or all(terminated):
+            infos[0]['metrics'] = self._episode_metrics()
+        return self._obs_list(self._h_obs), rewards, terminated, truncated, infos
+
+    def _episode_metrics(self):
+        """upstream wrappers/metrics.py values from the raw device counters."""
+        raw = self._engine.get_state(nat.STATE_METRICS)[0]
+        n = self.grid_config.num_agents
+        ot = self.grid_config.on_target
+        if ot == 'restart':
+            return {'avg_throughput': int(raw[0]) / self.grid_config.max_episode_steps}
+        if ot == 'nothing':
+            return {'ISR': float(int(raw[3])) / n, 'CSR': float(int(raw[3]) == n), 'ep_length': int(raw[2])}
+        return {'ISR': int(raw[0]) / n, 'CSR': float(int(raw[0]) == n), 'ep_length': int(raw[1]) / n + 1}
+
+    def sample_actions(self):
+        return self._multi_action_sampler.sample_actions(dim=self.grid_config.num_agents)
+
+    def get_num_agents(self):
+        return self.grid_config.num_agents
+
+    def get_agents_xy(self, only_active=False, ignore_borders=False):
+        return self.grid.get_agents_xy(only_active=only_active, ignore_borders=ignore_borders)
+
+    def get_targets_xy(self, only_active=False, ignore_borders=False):
+        return self.grid.get_targets_xy(only_active=only_active, ignore_borders=ignore_borders)
+
+    def get_obstacles(self, ignore_borders=False):
+        return self.grid.get_obstacles(ignore_borders=ignore_borders)
+
+    def get_state(self, ignore_borders=False, as_dict=False):
+        return self.grid.get_state(ignore_borders=ignore_borders, as_dict=as_dict)
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def render(self, mode='ansi'):
+        from .utils import render_grid
+        g = self.grid
+        return render_grid(g.obstacles, g.positions_xy, g.finishes_xy, g.is_active)
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+
+PogemaLifeLong = Pogema
+PogemaCoopFinish = Pogema
+
+
+def _make_pogema(grid_config):
+    return Pogema(grid_config)
+
+
+def make_pogema(grid_config=None, *args, **kwargs):
+    """upstream integrations/make_pogema.py :: make_pogema (== pogema_v0)."""
+    if grid_config is None:
+        grid_config = GridConfig(**kwargs)
+    elif isinstance(grid_config, dict):
+        grid_config = GridConfig(**grid_config)
+    if grid_config.integration in (None, 'gymnasium'):
+        return _make_pogema(grid_config)
+    if grid_config.integration == 'PettingZoo':
+        from .integrations.pettingzoo import parallel_env
+        return parallel_env(grid_config)
+    raise KeyError(f"integration {grid_config.integration!r} is out of scope of this engine "
+                   "(SampleFactory / PyMARL / rllib adapters wrap third-party libraries)")
+
+
+pogema_v0 = make_pogema

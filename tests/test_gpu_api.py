@@ -1,0 +1,201 @@
+"""GPU tests of the drop-in API surface: pogema_v0 lists, metrics, PettingZoo adapter, hand-derived
+scenarios, observation formats, checkpoint/resume, error behaviour."""
+import numpy as np
+import pytest
+
+from oracle import pogema_oracle as orc
+from tests.scenarios import SCENARIOS, clean_map
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("sc", SCENARIOS, ids=[s["name"] for s in SCENARIOS])
+@pytest.mark.parametrize("system", ["priority", "block_both", "soft"])
+def test_collision_scenarios_on_gpu(sc, system):
+    from pogema_b200 import GridConfig, pogema_v0
+    env = pogema_v0(GridConfig(map=clean_map(sc["map"]), obs_radius=2, collision_system=system,
+                               on_target="nothing", seed=0))
+    env.reset()
+    env.step(sc["actions"])
+    got = [tuple(p) for p in env.get_agents_xy(ignore_borders=True)]
+    assert got == sc["expect"][system]
+    env.close()
+
+
+@pytest.mark.parametrize("ot", ["finish", "nothing", "restart"])
+@pytest.mark.parametrize("coll", ["priority", "block_both", "soft"])
+def test_pogema_v0_matches_oracle_lists(coll, ot):
+    """Same calls, same return types and values as the (restated) reference, incl. infos and metrics."""
+    from pogema_b200 import GridConfig, pogema_v0
+    kw = dict(size=8, density=0.3, num_agents=4, obs_radius=5, max_episode_steps=16, collision_system=coll,
+              on_target=ot, seed=11)
+    env = pogema_v0(GridConfig(**kw))
+    ref = orc.pogema_v0(orc.GridConfig(**kw))
+    obs, infos = env.reset()
+    robs, rinfos = ref.reset()
+    assert isinstance(obs, list) and len(obs) == 4 and obs[0].dtype == np.float32 and obs[0].shape == (3, 11, 11)
+    assert all(np.array_equal(a, b) for a, b in zip(obs, robs)) and infos == rinfos
+    assert env.observation_space.shape == (3, 11, 11) and env.action_space.n == 5
+    for episode in range(2):
+        for t in range(16):
+            a = env.sample_actions()
+            assert np.array_equal(a, ref.sample_actions())          # same ActionsSampler stream
+            o, r, te, tr, inf = env.step(a)
+            ro, rr, rte, rtr, rinf = ref.step(a)
+            assert all(np.array_equal(x, y) for x, y in zip(o, ro))
+            assert r == rr and te == rte and tr == rtr
+            assert all(isinstance(v, float) for v in r) and all(isinstance(v, bool) for v in te + tr)
+            assert inf == rinf, (inf, rinf)
+            assert env.get_agents_xy() == ref.unwrapped.grid.get_agents_xy()
+            assert env.get_targets_xy(ignore_borders=True) == ref.unwrapped.grid.get_targets_xy(ignore_borders=True)
+            if all(te) or all(tr):
+                assert "metrics" in inf[0]
+                break
+        obs, infos = env.reset()
+        robs, rinfos = ref.reset()
+        assert all(np.array_equal(a, b) for a, b in zip(obs, robs))
+    assert np.array_equal(env.get_obstacles(), ref.unwrapped.grid.get_obstacles())
+    env.close()
+
+
+def test_parallel_env_dicts():
+    from pogema_b200 import GridConfig, parallel_env
+    env = parallel_env(GridConfig(size=8, num_agents=3, seed=2, max_episode_steps=5))
+    obs, infos = env.reset()
+    assert env.possible_agents == ["player_0", "player_1", "player_2"] and set(obs) == set(env.possible_agents)
+    for t in range(5):
+        obs, rew, term, trunc, infos = env.step({a: 0 for a in env.agents})
+    assert all(trunc.values()) and env.agents == []
+    env.close()
+
+
+def test_bits_format_equals_u8():
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    for r in (2, 5, 7):
+        gc = GridConfig(size=16, density=0.3, num_agents=20, obs_radius=r, max_episode_steps=32,
+                        collision_system="soft", on_target="restart", seed=1)
+        a = BatchedPogema(gc, num_envs=6, auto_reset=True)
+        b = BatchedPogema(gc, num_envs=6, auto_reset=True, obs_format="bits")
+        oa, ob = a.reset(), b.reset()
+        g = torch.Generator(device="cuda").manual_seed(0)
+        for t in range(40):
+            D = 2 * r + 1
+            bits = ob.cpu().numpy().view(np.uint32)
+            unpacked = np.unpackbits(bits.view(np.uint8), bitorder="little").reshape(6, 20, -1)[:, :, :3 * D * D]
+            assert np.array_equal(unpacked.reshape(6, 20, 3, D, D), oa.cpu().numpy())
+            act = a.sample_actions(g)
+            oa = a.step(act)[0]
+            ob = b.step(act)[0]
+
+
+def test_checkpoint_resume_and_host_step():
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    gc = GridConfig(size=16, density=0.3, num_agents=12, obs_radius=3, max_episode_steps=20,
+                    collision_system="priority", on_target="restart", seed=4)
+    env = BatchedPogema(gc, num_envs=5, auto_reset=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    acts = [env.sample_actions(g) for _ in range(30)]
+    for t in range(10):
+        env.step(acts[t])
+    sd = env.state_dict()
+    first = [tuple(x.clone() for x in env.step(acts[t])) for t in range(10, 30)]
+    env.load_state_dict(sd)
+    # resume through the C-ABI host-buffer call and compare with the device-pointer path
+    n, a = 5, 12
+    obs = np.empty(env.engine.obs_shape(), np.uint8)
+    rew = np.empty((n, a), np.float32)
+    te = np.empty((n, a), np.uint8)
+    tr = np.empty((n, a), np.uint8)
+    for t in range(10, 30):
+        env.engine.step_host(acts[t].cpu().numpy(), obs, rew, te, tr)
+        o, r, term, trunc = first[t - 10]
+        assert np.array_equal(obs, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy())
+        assert np.array_equal(te.astype(bool), term.cpu().numpy()) and np.array_equal(tr.astype(bool), trunc.cpu().numpy())
+
+
+def test_batched_metrics_match_oracle_wrappers():
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    for ot in ("finish", "nothing", "restart"):
+        kw = dict(size=8, density=0.2, num_agents=5, obs_radius=2, max_episode_steps=12, collision_system="priority",
+                  on_target=ot)
+        seeds = [0, 1, 2, 3]
+        env = BatchedPogema(GridConfig(**kw), num_envs=4, seeds=seeds, auto_reset=True)
+        env.reset()
+        refs = [orc.pogema_v0(orc.GridConfig(seed=s, **kw)) for s in seeds]
+        for r in refs:
+            r.reset()
+        rng = np.random.default_rng(0)
+        last = [None] * 4
+        for t in range(40):
+            acts = rng.integers(0, 5, size=(4, 5)).astype(np.uint8)
+            env.step(torch.from_numpy(acts).cuda())
+            done = env.episode_done.cpu().numpy()
+            for k, r in enumerate(refs):
+                _, _, te, tr, info = r.step(list(acts[k]))
+                fin = all(te) or all(tr)
+                assert bool(done[k]) == fin
+                if fin:
+                    last[k] = info[0]["metrics"]
+                    r.reset()
+            m = env.metrics()
+            for k in range(4):
+                if last[k] is not None:
+                    for key, val in last[k].items():
+                        assert m[key][k] == val, (ot, t, k, key, m[key][k], val)
+
+
+def test_error_behaviour():
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig, pogema_v0
+    with pytest.raises(OverflowError):
+        BatchedPogema(GridConfig(size=4, density=0.9, num_agents=8, seed=0), num_envs=2)
+    with pytest.raises(OverflowError):
+        pogema_v0(GridConfig(size=4, density=0.9, num_agents=8, seed=0)).reset()
+    env = BatchedPogema(GridConfig(size=8, num_agents=2, seed=0), num_envs=2)
+    env.reset()
+    env.step(torch.full((2, 2), 7, dtype=torch.uint8, device="cuda"))
+    with pytest.raises(IndexError):
+        env.check_errors()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((3, 2), dtype=torch.uint8, device="cuda"))
+    single = pogema_v0(GridConfig(size=8, num_agents=2, seed=0))
+    single.reset()
+    with pytest.raises(IndexError):
+        single.step([5, 0])
+    with pytest.raises(AssertionError):
+        single.step([0])
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int32", "int64"])
+def test_action_dtypes(dtype):
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    gc = GridConfig(size=10, num_agents=6, seed=3, obs_radius=2)
+    a = BatchedPogema(gc, num_envs=3)
+    b = BatchedPogema(gc, num_envs=3)
+    a.reset(), b.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(10):
+        act = a.sample_actions(g)
+        oa = a.step(act)[0]
+        ob = b.step(act.to(getattr(torch, dtype)))[0]
+        assert torch.equal(oa, ob)
+
+
+def test_explicit_agents_on_generated_map():
+    from pogema_b200 import GridConfig, pogema_v0
+    kw = dict(size=8, density=0.3, seed=9, agents_xy=[[0, 0], [7, 7]], targets_xy=[[3, 3], [4, 4]], obs_radius=3)
+    env = pogema_v0(GridConfig(**kw))
+    ref = orc.pogema_v0(orc.GridConfig(**kw))
+    obs, _ = env.reset()
+    robs, _ = ref.reset()
+    assert all(np.array_equal(a, b) for a, b in zip(obs, robs))
+    for t in range(12):
+        a = ref.sample_actions()
+        o, r, te, tr, _ = env.step(a)
+        ro, rr, rte, rtr, _ = ref.step(a)
+        assert all(np.array_equal(x, y) for x, y in zip(o, ro)) and r == rr and te == rte
