@@ -380,7 +380,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <int TEAM, int COLL, int OP, int RT>
-__global__ void __launch_bounds__((TEAM < 128 ? 1024 : TEAM), (TEAM < 128 ? 1 : (TEAM <= 512 ? 1024 / TEAM : 1)))
+__global__ void __launch_bounds__(1024, 1)
     pgm_step_kernel(const StepArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int team = threadIdx.x / TEAM;

@@ -46,8 +46,9 @@ def test_pogema_v0_matches_oracle_lists(coll, ot):
             assert r == rr and te == rte and tr == rtr
             assert all(isinstance(v, float) for v in r) and all(isinstance(v, bool) for v in te + tr)
             assert inf == rinf, (inf, rinf)
-            assert env.get_agents_xy() == ref.unwrapped.grid.get_agents_xy()
-            assert env.get_targets_xy(ignore_borders=True) == ref.unwrapped.grid.get_targets_xy(ignore_borders=True)
+            assert [tuple(p) for p in env.get_agents_xy()] == [tuple(p) for p in ref.unwrapped.grid.get_agents_xy()]
+            assert ([tuple(p) for p in env.get_targets_xy(ignore_borders=True)] ==
+                    [tuple(p) for p in ref.unwrapped.grid.get_targets_xy(ignore_borders=True)])
             if all(te) or all(tr):
                 assert "metrics" in inf[0]
                 break
