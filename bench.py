@@ -222,17 +222,35 @@ def run_cuda(args):
     ring = [env.new_obs_buffer() for _ in range(4)]
     stream = torch.cuda.current_stream(dev)
 
-    # The K timed steps are issued as replays of a CUDA graph holding GRAPH_STEPS consecutive
-    # step launches (launch-bound inner loop -> graph), plus K % GRAPH_STEPS plain launches.
+    # The K timed steps are issued as launches of SPL consecutive steps each (pgm_step_many: one kernel
+    # advances every instance by SPL steps on its own timeline, all per-step outputs are written), plus
+    # K % SPL single-step launches.  --steps-per-launch 1 times the closed-loop form instead: one launch
+    # per step, replayed from a CUDA graph (or launched from Python with --no-graph).
+    SPL = max(1, args.steps_per_launch)
     GRAPH_STEPS = n_act
+    ring_t = torch.stack(ring)                      # [4, N, A, 3, D, D] observation ring, 4 x 95 MB > L2
+    ring = [ring_t[i] for i in range(4)]
+    act_t = torch.stack(acts)                       # [16, N, A]
+    rew_t = torch.empty((SPL, N, A), dtype=torch.float32, device=dev)
+    term_t = torch.empty((SPL, N, A), dtype=torch.bool, device=dev)
+    trunc_t = torch.empty((SPL, N, A), dtype=torch.bool, device=dev)
+    act_many = act_t[torch.arange(SPL, device=dev) % n_act].contiguous() if SPL > 1 else None
+    sptr = int(stream.cuda_stream)
 
     def plain_steps(first, count):
         for i in range(first, first + count):
             env.step(acts[i % n_act], out=ring[i % 4])
 
+    def many_steps(launches):
+        for _ in range(launches):
+            env.engine.step_many(SPL, act_many.data_ptr(), 1, ring_t.data_ptr(), 4, rew_t.data_ptr(),
+                                 term_t.data_ptr(), trunc_t.data_ptr(), sptr)
+
     plain_steps(0, max(args.warmup, 3))
     graph = None
-    if not args.no_graph:
+    if SPL > 1:
+        many_steps(2)
+    elif not args.no_graph:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
@@ -251,7 +269,10 @@ def run_cuda(args):
     launches0 = env.engine.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    if graph is not None:
+    if SPL > 1:
+        many_steps(args.steps // SPL)
+        plain_steps(0, args.steps % SPL)
+    elif graph is not None:
         for _ in range(args.steps // GRAPH_STEPS):
             graph.replay()
         plain_steps(0, args.steps % GRAPH_STEPS)
@@ -270,6 +291,31 @@ def run_cuda(args):
     env.check_errors()
     ms_per_step = ms_total / args.steps
     value = world * N * A * args.steps / (ms_total * 1e-3)
+
+    # ---- closed-loop form for comparison: one kernel launch per step (what an RL loop with a policy in
+    # between would issue), replayed from a CUDA graph
+    closed_loop = None
+    if world == 1 and SPL > 1 and not args.no_graph:
+        torch.cuda.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g2, stream=side):
+                plain_steps(0, GRAPH_STEPS)
+        stream.wait_stream(side)
+        g2.replay()
+        torch.cuda.synchronize()
+        reps = max(1, min(args.steps, 2048) // GRAPH_STEPS)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(reps):
+            g2.replay()
+        c1.record(stream)
+        torch.cuda.synchronize()
+        cl_ms = c0.elapsed_time(c1) / (reps * GRAPH_STEPS)
+        closed_loop = {"value": N * A / (cl_ms * 1e-3), "unit": UNIT, "ms_per_step": cl_ms, "steps": reps * GRAPH_STEPS,
+                       "launch": "one kernel launch per step (pgm_step), CUDA graph of %d launches replayed" % GRAPH_STEPS}
 
     # ---- e2e: the C-ABI host-buffer call (pgm_step_host), H2D actions + D2H obs/rewards/flags every step
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
@@ -313,15 +359,19 @@ def run_cuda(args):
             "config": {"workload": WORKLOAD_NAME, "instances_per_gpu": N, "agents_per_instance": A,
                        "obs": "uint8 [N,A,3,11,11]", "actions": "uint8 resident in HBM, 16 pre-generated tensors",
                        "l2": "obs written to a ring of 4 buffers (4 x %.0f MB > 126 MB L2)" % (env.engine.obs_bytes / 1e6),
-                       "launch": ("CUDA graph of %d step launches, replayed" % GRAPH_STEPS) if graph is not None else "one pgm_step call per step",
+                       "launch": ("pgm_step_many: %d steps per kernel launch (every step writes all its outputs)" % SPL) if SPL > 1
+                       else (("one launch per step, CUDA graph of %d launches replayed" % GRAPH_STEPS) if graph is not None else "one pgm_step call per step"),
+                       "steps_per_launch": SPL,
                        "plan": env.engine.plan(), "parallelism": f"instances sharded over {world} GPU(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_agent_step": bpa, "kernel": "pgm_step_kernel (one launch per step)"},
+                         "algorithmic_bytes_per_agent_step": bpa, "kernel": "pgm_step_kernel (%d step(s) per launch)" % SPL,
+                         "algorithmic_bytes_per_launch": N * A * bpa * SPL},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "pgm_step_host (C-ABI, pinned host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "closed_loop": closed_loop,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -345,6 +395,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--steps-per-launch", type=int, default=16,
+                    help="steps advanced by one kernel launch (pgm_step_many); 1 = one launch per step")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graph replays")
     args = ap.parse_args()
     if args.warmup < 3:

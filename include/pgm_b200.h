@@ -169,6 +169,18 @@ int pgm_step(pgm_engine* e, const void* actions_dev, int32_t action_itemsize, vo
              float* rewards_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream);
 
 /*
+ * K consecutive steps in ONE launch for action tensors that are known in advance (open-loop
+ * rollouts, random-policy data collection): exactly the results of K pgm_step calls, but every
+ * instance runs its own timeline - no grid-wide barrier between steps, the map stays in shared
+ * memory, the observation stores of one instance overlap the move phases of the others.
+ *   actions_dev:  [K][N][A]        rewards/terminated/truncated_dev: [K][N][A]
+ *   obs_dev:      [obs_ring][N][A]... step k writes slot k % obs_ring (NULL skips observations)
+ */
+int pgm_step_many(pgm_engine* e, int32_t num_steps, const void* actions_dev, int32_t action_itemsize,
+                  void* obs_dev, int32_t obs_ring, float* rewards_dev, uint8_t* terminated_dev,
+                  uint8_t* truncated_dev, void* stream);
+
+/*
  * Same step with HOST buffers: copies actions host->device, launches the step,
  * copies obs / rewards / flags device->host and synchronises the stream.  Host
  * buffers may be pageable or pinned (pinned is faster).  obs_host may be NULL.

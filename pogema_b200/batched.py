@@ -111,6 +111,28 @@ class BatchedPogema:
                          self._stream())
         return obs, self._rewards, self._terminated, self._truncated
 
+    def rollout(self, actions: torch.Tensor, obs_out: Optional[torch.Tensor] = None, compute_obs: bool = True):
+        """K consecutive steps in ONE kernel launch (``pgm_step_many``) for actions known in advance.
+
+        actions: int tensor [K, N, A].  Returns (obs [R, N, A, ...], rewards [K, N, A], terminated [K, N, A],
+        truncated [K, N, A]); step k writes observation slot ``k % R`` where R = ``obs_out.shape[0]`` (default:
+        R = K, every step's observation is kept).  Results are identical to K ``step`` calls."""
+        if actions.device != self.device or actions.dim() != 3 or tuple(actions.shape[1:]) != (self.num_envs, self.num_agents):
+            raise ValueError(f"actions must be a [K, {self.num_envs}, {self.num_agents}] tensor on {self.device}")
+        actions = actions.contiguous()
+        K = actions.shape[0]
+        with torch.cuda.device(self.device):
+            if obs_out is None and compute_obs:
+                e = self.engine
+                obs_out = torch.empty((K,) + tuple(e.obs_shape()), dtype=self._obs.dtype, device=self.device)
+            rew = torch.empty((K, self.num_envs, self.num_agents), dtype=torch.float32, device=self.device)
+            term = torch.empty((K, self.num_envs, self.num_agents), dtype=torch.bool, device=self.device)
+            trunc = torch.empty((K, self.num_envs, self.num_agents), dtype=torch.bool, device=self.device)
+        ring = int(obs_out.shape[0]) if compute_obs else 1
+        self.engine.step_many(K, actions.data_ptr(), actions.element_size(), obs_out.data_ptr() if compute_obs else 0,
+                              ring, rew.data_ptr(), term.data_ptr(), trunc.data_ptr(), self._stream())
+        return obs_out, rew, term, trunc
+
     def sample_actions(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         return torch.randint(0, 5, (self.num_envs, self.num_agents), dtype=torch.uint8, device=self.device,
                              generator=generator)

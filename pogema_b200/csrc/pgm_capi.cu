@@ -143,9 +143,9 @@ int compute_plan(pgm_engine* e) {
   L.team_smem = round_up(off, 16);
   if (L.team_smem > smem_max)
     return fail(PGM_ERR_UNSUPPORTED, "instance needs %d bytes of shared memory (max %d)", L.team_smem, smem_max);
-  // teams per CTA: about half of the teams an SM hosts (two CTAs per SM), fewer launches of larger CTAs
+  // teams per CTA: about a quarter of the teams an SM hosts (four CTAs per SM)
   const int per_sm_teams = (c.num_envs + e->sm_count - 1) / e->sm_count;
-  int tpc = std::max(1, std::min(16, (per_sm_teams + 1) / 2));
+  int tpc = std::max(1, std::min(16, (per_sm_teams + 3) / 4));
   tpc = std::max(tpc, std::min(4, 128 / team));
   if (const char* v = getenv("PGM_TPC")) tpc = std::max(1, atoi(v));  // tuning knob
   tpc = std::min(tpc, 1024 / team);
@@ -212,6 +212,11 @@ StepArgs make_args(pgm_engine* e) {
   a.metric_last = e->d_mlast;
   a.actions = nullptr;
   a.act_itemsize = 1;
+  a.num_steps = 1;
+  a.act_step_stride = 0;
+  a.out_step_stride = 0;
+  a.obs_ring = 1;
+  a.obs_slot_stride = 0;
   a.obs = nullptr;
   a.obs_inst_stride = e->obs_inst_stride;
   a.rewards = nullptr;
@@ -552,6 +557,33 @@ int pgm_step(pgm_engine* e, const void* actions_dev, int32_t action_itemsize, vo
   a.actions = (const uint8_t*)actions_dev;
   a.act_itemsize = action_itemsize;
   a.obs = (uint8_t*)obs_dev;
+  a.rewards = rewards_dev;
+  a.terminated = terminated_dev;
+  a.truncated = truncated_dev;
+  return launch(e, a, OP_STEP, (cudaStream_t)stream);
+}
+
+int pgm_step_many(pgm_engine* e, int32_t num_steps, const void* actions_dev, int32_t action_itemsize, void* obs_dev,
+                  int32_t obs_ring, float* rewards_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                  void* stream) {
+  if (!e || !actions_dev || !rewards_dev || !terminated_dev || !truncated_dev)
+    return fail(PGM_ERR_INVALID, "null argument");
+  if (num_steps < 1) return fail(PGM_ERR_INVALID, "num_steps must be >= 1");
+  if (action_itemsize != 1 && action_itemsize != 2 && action_itemsize != 4 && action_itemsize != 8)
+    return fail(PGM_ERR_INVALID, "action_itemsize must be 1, 2, 4 or 8");
+  if (obs_dev && obs_ring < 1) return fail(PGM_ERR_INVALID, "obs_ring must be >= 1");
+  if (!e->tasks_ready) return fail(PGM_ERR_STATE, "pgm_step_many before pgm_generate / pgm_set_tasks");
+  DeviceGuard guard(e->cfg.device);
+  const long long NA = (long long)e->cfg.num_envs * e->cfg.num_agents;
+  StepArgs a = make_args(e);
+  a.actions = (const uint8_t*)actions_dev;
+  a.act_itemsize = action_itemsize;
+  a.num_steps = num_steps;
+  a.act_step_stride = NA * action_itemsize;
+  a.out_step_stride = NA;
+  a.obs = (uint8_t*)obs_dev;
+  a.obs_ring = obs_dev ? obs_ring : 1;
+  a.obs_slot_stride = e->obs_bytes;
   a.rewards = rewards_dev;
   a.terminated = terminated_dev;
   a.truncated = truncated_dev;

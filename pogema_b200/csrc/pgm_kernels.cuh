@@ -64,6 +64,11 @@ struct StepArgs {
   // io
   const uint8_t* actions;
   int act_itemsize;
+  int num_steps;               // steps advanced by this launch (pgm_step_many)
+  long long act_step_stride;   // bytes between the action tensors of consecutive steps
+  long long out_step_stride;   // elements between rewards/terminated/truncated of consecutive steps
+  int obs_ring;                // step k writes observation slot k % obs_ring
+  long long obs_slot_stride;   // bytes between observation slots
   uint8_t* obs;
   long long obs_inst_stride;  // bytes
   float* rewards;
@@ -285,7 +290,8 @@ __device__ __forceinline__ void agent_bits_static(const uint32_t* s_obst, const 
   } while (0)
 
 template <int TEAM, int RT>
-__device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int tid, int bar_id, const uint32_t* s_obst,
+__device__ __forceinline__ void emit_observations(const StepArgs& p, uint8_t* obs, int n, int tid, int bar_id,
+                                                  const uint32_t* s_obst,
                                                   const uint32_t* s_abits, uint32_t* stage, const uint32_t* s_npos,
                                                   const uint32_t* s_tgt) {
   const int r = (RT > 0) ? RT : p.r;
@@ -320,10 +326,10 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, int n, int 
     // ---- write out
     if (p.obs_format == 1) {
       const int wpa = sbpa >> 5;
-      uint32_t* out = reinterpret_cast<uint32_t*>(p.obs + (long long)n * p.obs_inst_stride) + (long long)g0 * wpa;
+      uint32_t* out = reinterpret_cast<uint32_t*>(obs + (long long)n * p.obs_inst_stride) + (long long)g0 * wpa;
       for (int w = tid; w < gcount * wpa; w += TEAM) __stcs(out + w, stage[w]);
     } else {
-      uint8_t* out = p.obs + (long long)n * p.obs_inst_stride + (long long)g0 * bpa;
+      uint8_t* out = obs + (long long)n * p.obs_inst_stride + (long long)g0 * bpa;
       const int nbytes = gcount * bpa;
       int head = (int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
       head = min(head, nbytes);
@@ -408,29 +414,16 @@ __global__ void __launch_bounds__(1024, 1)
 
   // Let the next launch in the stream be scheduled as soon as SM resources free up: its
   // prologue (phase 0a) overlaps this grid's tail; its griddepcontrol.wait still waits for
-  // this grid to complete and flush, so there is no cross-step race on any buffer.
+  // this grid to complete and flush, so there is no cross-launch race on any buffer.
   pdl_trigger();
   PGM_STAMP(0);
-  // ---- phase 0a (independent of the previous step): obstacle map by bulk copy, fills
+  // ---- phase 0a (independent of the previous launch): obstacle map by bulk copy
   if (tid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
-    s_cnt[0] = 0;
-    s_cnt[1] = 0;
     const uint32_t bytes = (uint32_t)p.obst_stride * 4u;
     mbar_expect_tx(s_bar, bytes);
     bulk_g2s(s_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
-  }
-  {
-    // both regions are padded to multiples of 16 bytes by the host-side layout
-    const int abits_vec = (p.PH * WPR + 1 + 3) >> 2;
-    uint4* a4 = reinterpret_cast<uint4*>(s_abits);
-    for (int w = tid; w < abits_vec; w += TEAM) a4[w] = make_uint4(0u, 0u, 0u, 0u);
-    if (OP == OP_STEP) {
-      const int occ_vec = (p.PH * PW * 2 + 4 + 15) >> 4;
-      uint4* o4 = reinterpret_cast<uint4*>(s_occ);
-      for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
   }
   // ---- phase 0b: mutable state of this instance (two agents per thread in flight)
   PGM_STAMP(1);
@@ -451,16 +444,6 @@ __global__ void __launch_bounds__(1024, 1)
     const bool has1 = a1 < A;
     uint2 w0 = src[ia + a0];
     uint2 w1 = has1 ? src[ia + a1] : make_uint2(0u, 0u);
-    uint32_t act0 = 0u, act1 = 0u;
-    if (OP == OP_STEP) {
-      act0 = p.actions[(ia + a0) * p.act_itemsize];
-      if (has1) act1 = p.actions[(ia + a1) * p.act_itemsize];
-      if (act0 > 4u || act1 > 4u) {
-        atomicOr(p.err_flag, 1);
-        if (act0 > 4u) act0 = 0u;
-        if (act1 > 4u) act1 = 0u;
-      }
-    }
     if (OP == OP_RESET) {
       w0.x |= 0x8000u;
       w1.x |= 0x8000u;
@@ -469,202 +452,251 @@ __global__ void __launch_bounds__(1024, 1)
     s_npos[a0] = st_pos(w0.x);
     s_tgt[a0] = w0.y;
     s_flag[a0] = (uint8_t)st_active(w0.x);
-    if (OP == OP_STEP) s_act[a0] = (uint8_t)act0;
     if (has1) {
       s_pos[a1] = st_pos(w1.x);
       s_npos[a1] = st_pos(w1.x);
       s_tgt[a1] = w1.y;
       s_flag[a1] = (uint8_t)st_active(w1.x);
-      if (OP == OP_STEP) s_act[a1] = (uint8_t)act1;
     }
   }
-  team_sync<TEAM>(bar_id);
+  mbar_wait(s_bar, 0);
 
-  if (OP == OP_STEP) {
-    // ---- phase 1: pre-move occupancy grid (active agents only) ------------
-    for (int a = tid; a < A; a += TEAM) {
-      if (s_flag[a] & 1u) {
-        const uint32_t pp = s_pos[a];
-        s_occ[(pp & 0xFFFF) * PW + (pp >> 16)] = (uint16_t)a;
+  // One launch advances this instance by p.num_steps steps (1 for pgm_step; >1 for pgm_step_many,
+  // where every team runs its own timeline: no grid-wide barrier between steps, the observation
+  // stores of one instance overlap the move phases of the others).
+  const int num_steps = (OP == OP_STEP) ? p.num_steps : 1;
+#pragma unroll 1
+  for (int k = 0; k < num_steps; ++k) {
+    // ---- per-step fills (both regions are padded to multiples of 16 bytes by the host-side layout)
+    {
+      const int abits_vec = (p.PH * WPR + 1 + 3) >> 2;
+      uint4* a4 = reinterpret_cast<uint4*>(s_abits);
+      for (int w = tid; w < abits_vec; w += TEAM) a4[w] = make_uint4(0u, 0u, 0u, 0u);
+      if (OP == OP_STEP) {
+        const int occ_vec = (p.PH * PW * 2 + 4 + 15) >> 4;
+        uint4* o4 = reinterpret_cast<uint4*>(s_occ);
+        for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (tid == 0) {
+          s_cnt[0] = 0;
+          s_cnt[1] = 0;
+        }
       }
     }
+    uint8_t* obs_k = p.obs;
+    if (OP == OP_STEP) {
+      // actions of step k
+      const uint8_t* act_k = p.actions + (long long)k * p.act_step_stride;
+      for (int a0 = tid; a0 < A; a0 += 2 * TEAM) {
+        const int a1 = a0 + TEAM;
+        const bool has1 = a1 < A;
+        uint32_t act0 = act_k[(ia + a0) * p.act_itemsize];
+        uint32_t act1 = has1 ? act_k[(ia + a1) * p.act_itemsize] : 0u;
+        if (act0 > 4u || act1 > 4u) {
+          atomicOr(p.err_flag, 1);
+          if (act0 > 4u) act0 = 0u;
+          if (act1 > 4u) act1 = 0u;
+        }
+        s_act[a0] = (uint8_t)act0;
+        if (has1) s_act[a1] = (uint8_t)act1;
+      }
+      if (p.obs != nullptr) obs_k = p.obs + (long long)(k % p.obs_ring) * p.obs_slot_stride;
+    }
     team_sync<TEAM>(bar_id);
-    mbar_wait(s_bar, 0);
-    PGM_STAMP(3);
 
-    // ---- phase 2: move resolution -----------------------------------------
-    if (COLL == 2) {
-      // soft, pass A: moves into obstacles and edge swaps become 'stay'
+    if (OP == OP_STEP) {
+      // ---- phase 1: pre-move occupancy grid (active agents only) ------------
       for (int a = tid; a < A; a += TEAM) {
-        uint32_t eff = 0u;
+        if (s_flag[a] & 1u) {
+          const uint32_t pp = s_pos[a];
+          s_occ[(pp & 0xFFFF) * PW + (pp >> 16)] = (uint16_t)a;
+        }
+      }
+      team_sync<TEAM>(bar_id);
+      PGM_STAMP(3);
+
+      // ---- phase 2: move resolution -----------------------------------------
+      if (COLL == 2) {
+        // soft, pass A: moves into obstacles and edge swaps become 'stay'
+        for (int a = tid; a < A; a += TEAM) {
+          uint32_t eff = 0u;
+          const uint32_t act = s_act[a];
+          if ((s_flag[a] & 1u) && act != 0u) {
+            const uint32_t pp = s_pos[a];
+            const int tx = (int)(pp & 0xFFFF) + move_dx(act), ty = (int)(pp >> 16) + move_dy(act);
+            eff = act;
+            if (bit_at(s_obst, WPR, tx, ty)) {
+              eff = 0u;
+            } else {
+              const uint32_t j = s_occ[tx * PW + ty];
+              if (j != OCC_NONE && s_act[j] == opposite(act)) eff = 0u;
+            }
+          }
+          s_link[a] = eff;  // temporarily: effective action
+        }
+        team_sync<TEAM>(bar_id);
+        // the effective actions replace the raw ones (each thread rewrites its own entries)
+        for (int a = tid; a < A; a += TEAM) s_act[a] = (uint8_t)s_link[a];
+        team_sync<TEAM>(bar_id);
+      }
+      bool pend = false;
+      for (int a = tid; a < A; a += TEAM) {
+        uint32_t link = ST_FAIL;
         const uint32_t act = s_act[a];
         if ((s_flag[a] & 1u) && act != 0u) {
           const uint32_t pp = s_pos[a];
-          const int tx = (int)(pp & 0xFFFF) + move_dx(act), ty = (int)(pp >> 16) + move_dy(act);
-          eff = act;
-          if (bit_at(s_obst, WPR, tx, ty)) {
-            eff = 0u;
-          } else {
+          const int sx = pp & 0xFFFF, sy = pp >> 16;
+          const int tx = sx + move_dx(act), ty = sy + move_dy(act);
+          if (!bit_at(s_obst, WPR, tx, ty)) {
             const uint32_t j = s_occ[tx * PW + ty];
-            if (j != OCC_NONE && s_act[j] == opposite(act)) eff = 0u;
-          }
-        }
-        s_link[a] = eff;  // temporarily: effective action
-      }
-      team_sync<TEAM>(bar_id);
-      // the effective actions replace the raw ones (each thread rewrites its own entries)
-      for (int a = tid; a < A; a += TEAM) s_act[a] = (uint8_t)s_link[a];
-      team_sync<TEAM>(bar_id);
-    }
-    bool pend = false;
-    for (int a = tid; a < A; a += TEAM) {
-      uint32_t link = ST_FAIL;
-      const uint32_t act = s_act[a];
-      if ((s_flag[a] & 1u) && act != 0u) {
-        const uint32_t pp = s_pos[a];
-        const int sx = pp & 0xFFFF, sy = pp >> 16;
-        const int tx = sx + move_dx(act), ty = sy + move_dy(act);
-        if (!bit_at(s_obst, WPR, tx, ty)) {
-          const uint32_t j = s_occ[tx * PW + ty];
-          if (COLL == 1) {
-            // block_both: free cell, sole claimant
-            if (j == OCC_NONE && !other_claimant<0>(s_occ, s_act, PW, tx, ty, sx, sy, 0, 0)) link = ST_OK;
-          } else if (COLL == 0) {
-            // priority: occupant must have a lower index and leave; first claimant above it wins
-            bool ok = true;
-            int lo = -1;
-            if (j != OCC_NONE) {
-              if ((int)j > a || s_act[j] == 0) ok = false;
-              else lo = (int)j;
+            if (COLL == 1) {
+              // block_both: free cell, sole claimant
+              if (j == OCC_NONE && !other_claimant<0>(s_occ, s_act, PW, tx, ty, sx, sy, 0, 0)) link = ST_OK;
+            } else if (COLL == 0) {
+              // priority: occupant must have a lower index and leave; first claimant above it wins
+              bool ok = true;
+              int lo = -1;
+              if (j != OCC_NONE) {
+                if ((int)j > a || s_act[j] == 0) ok = false;
+                else lo = (int)j;
+              }
+              if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, lo, a)) ok = false;
+              if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
+            } else {
+              // soft: no stayer on the cell, lowest-index claimant, occupant must leave
+              bool ok = !(j != OCC_NONE && s_act[j] == 0);
+              if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, -1, a)) ok = false;
+              if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
             }
-            if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, lo, a)) ok = false;
-            if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
-          } else {
-            // soft: no stayer on the cell, lowest-index claimant, occupant must leave
-            bool ok = !(j != OCC_NONE && s_act[j] == 0);
-            if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, -1, a)) ok = false;
-            if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
           }
         }
+        s_link[a] = link;
+        pend |= ((link & 3u) == ST_PEND);
       }
-      s_link[a] = link;
-      pend |= ((link & 3u) == ST_PEND);
-    }
-    if (COLL != 1) {
-      // pointer jumping along occupant chains; what is still pending after
-      // max_rounds is a rotation cycle (soft only) and succeeds
-      int rounds = 0;
-      while (team_any<TEAM>(bar_id, pend)) {
-        if (++rounds > p.max_rounds) break;
-        pend = false;
-        for (int a = tid; a < A; a += TEAM) {
-          const uint32_t l = s_link[a];
-          if ((l & 3u) == ST_PEND) {
-            const uint32_t lp = s_link[l >> 2];
-            const uint32_t nl = ((lp & 3u) == ST_PEND) ? (ST_PEND | (lp & ~3u)) : (lp & 3u);
-            s_link[a] = nl;
-            pend |= ((nl & 3u) == ST_PEND);
+      if (COLL != 1) {
+        // pointer jumping along occupant chains; what is still pending after
+        // max_rounds is a rotation cycle (soft only) and succeeds
+        int rounds = 0;
+        while (team_any<TEAM>(bar_id, pend)) {
+          if (++rounds > p.max_rounds) break;
+          pend = false;
+          for (int a = tid; a < A; a += TEAM) {
+            const uint32_t l = s_link[a];
+            if ((l & 3u) == ST_PEND) {
+              const uint32_t lp = s_link[l >> 2];
+              const uint32_t nl = ((lp & 3u) == ST_PEND) ? (ST_PEND | (lp & ~3u)) : (lp & 3u);
+              s_link[a] = nl;
+              pend |= ((nl & 3u) == ST_PEND);
+            }
           }
         }
-      }
-    }
-    team_sync<TEAM>(bar_id);
-    PGM_STAMP(4);
-
-    // ---- phase 3: apply moves, on_target bookkeeping, time limit -----------
-    int c_on = 0, c_was = 0;
-    for (int a = tid; a < A; a += TEAM) {
-      const uint32_t act = s_act[a];
-      uint32_t pp = s_pos[a];
-      if ((s_link[a] & 3u) != ST_FAIL) {
-        const int tx = (int)(pp & 0xFFFF) + move_dx(act), ty = (int)(pp >> 16) + move_dy(act);
-        pp = (uint32_t)tx | ((uint32_t)ty << 16);
-      }
-      s_npos[a] = pp;
-      const uint32_t on = (pp == s_tgt[a]) ? 1u : 0u;
-      const uint32_t fl = s_flag[a] & 1u;
-      const uint32_t was = on & fl;
-      s_flag[a] = (uint8_t)(fl | (on << 1) | (was << 2));
-      c_on += on;
-      c_was += was;
-    }
-    c_on = __reduce_add_sync(0xffffffffu, c_on);
-    c_was = __reduce_add_sync(0xffffffffu, c_was);
-    if (TEAM > 32) {
-      if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_cnt[0], c_on);
-        atomicAdd(&s_cnt[1], c_was);
       }
       team_sync<TEAM>(bar_id);
-      c_on = s_cnt[0];
-      c_was = s_cnt[1];
-    }
-    // (all reads of occ are done: the barrier after pointer jumping; stage may reuse it)
-    const bool trunc = (step_idx + 1 >= p.max_steps);
-    const bool solved = (c_was == A);
-    const bool all_term = (ONTGT == 2) ? false : (c_on == A);
-    const bool done = trunc || all_term;
-    const bool do_reset = done && p.auto_reset;
+      PGM_STAMP(4);
 
-    for (int a = tid; a < A; a += TEAM) {
-      const uint32_t f = s_flag[a];
-      const uint32_t fl = f & 1u, on = (f >> 1) & 1u, was = (f >> 2) & 1u;
-      float rew;
-      uint8_t term;
-      uint32_t nfl = fl;
-      uint32_t tt = s_tgt[a];
-      if (ONTGT == 0) {  // finish: reward once, agent disappears
-        rew = was ? 1.0f : 0.0f;
-        term = (uint8_t)on;
-        nfl = fl & (on ^ 1u);
-      } else if (ONTGT == 1) {  // nothing (cooperative finish)
-        rew = solved ? 1.0f : 0.0f;
-        term = solved ? 1 : 0;
-      } else {  // restart (lifelong): new target from the agent's own generator
-        rew = was ? 1.0f : 0.0f;
-        term = 0;
-        if (on && !do_reset) {
-          Pcg64 g = p.rng[ia + a];
-          const uint32_t k = pcg64_bounded32(g, (uint32_t)(p.comp_size[ia + a] - 1));
-          tt = p.cells[(long long)n * p.cells_stride + p.comp_start[ia + a] + k];
-          p.rng[ia + a] = g;
+      // ---- phase 3: apply moves, on_target bookkeeping, time limit -----------
+      int c_on = 0, c_was = 0;
+      for (int a = tid; a < A; a += TEAM) {
+        const uint32_t act = s_act[a];
+        uint32_t pp = s_pos[a];
+        if ((s_link[a] & 3u) != ST_FAIL) {
+          const int tx = (int)(pp & 0xFFFF) + move_dx(act), ty = (int)(pp >> 16) + move_dy(act);
+          pp = (uint32_t)tx | ((uint32_t)ty << 16);
+        }
+        s_npos[a] = pp;
+        const uint32_t on = (pp == s_tgt[a]) ? 1u : 0u;
+        const uint32_t fl = s_flag[a] & 1u;
+        const uint32_t was = on & fl;
+        s_flag[a] = (uint8_t)(fl | (on << 1) | (was << 2));
+        c_on += on;
+        c_was += was;
+      }
+      c_on = __reduce_add_sync(0xffffffffu, c_on);
+      c_was = __reduce_add_sync(0xffffffffu, c_was);
+      if (TEAM > 32) {
+        if ((threadIdx.x & 31) == 0) {
+          atomicAdd(&s_cnt[0], c_on);
+          atomicAdd(&s_cnt[1], c_was);
+        }
+        team_sync<TEAM>(bar_id);
+        c_on = s_cnt[0];
+        c_was = s_cnt[1];
+      }
+      // (all reads of occ are done: the barrier after pointer jumping; stage may reuse it)
+      const bool trunc = (step_idx + 1 >= p.max_steps);
+      const bool solved = (c_was == A);
+      const bool all_term = (ONTGT == 2) ? false : (c_on == A);
+      const bool done = trunc || all_term;
+      const bool do_reset = done && p.auto_reset;
+      const long long oa = ia + (long long)k * p.out_step_stride;  // outputs of step k
+
+      for (int a = tid; a < A; a += TEAM) {
+        const uint32_t f = s_flag[a];
+        const uint32_t fl = f & 1u, on = (f >> 1) & 1u, was = (f >> 2) & 1u;
+        float rew;
+        uint8_t term;
+        uint32_t nfl = fl;
+        uint32_t tt = s_tgt[a];
+        if (ONTGT == 0) {  // finish: reward once, agent disappears
+          rew = was ? 1.0f : 0.0f;
+          term = (uint8_t)on;
+          nfl = fl & (on ^ 1u);
+        } else if (ONTGT == 1) {  // nothing (cooperative finish)
+          rew = solved ? 1.0f : 0.0f;
+          term = solved ? 1 : 0;
+        } else {  // restart (lifelong): new target from the agent's own generator
+          rew = was ? 1.0f : 0.0f;
+          term = 0;
+          if (on && !do_reset) {
+            Pcg64 g = p.rng[ia + a];
+            const uint32_t kk = pcg64_bounded32(g, (uint32_t)(p.comp_size[ia + a] - 1));
+            tt = p.cells[(long long)n * p.cells_stride + p.comp_start[ia + a] + kk];
+            p.rng[ia + a] = g;
+          }
+        }
+        p.rewards[oa + a] = rew;
+        p.terminated[oa + a] = term;
+        p.truncated[oa + a] = trunc ? 1 : 0;
+        p.was_on_goal[ia + a] = (uint8_t)was;
+        uint32_t pp = s_npos[a];
+        if (do_reset) {
+          const uint2 w = p.state0[ia + a];
+          pp = st_pos(w.x);
+          tt = w.y;
+          nfl = 1u;
+          if (ONTGT == 2) p.rng[ia + a] = p.rng0[ia + a];
+        }
+        s_npos[a] = pp;
+        s_pos[a] = pp;  // next step of a multi-step launch starts here
+        s_tgt[a] = tt;
+        s_flag[a] = (uint8_t)nfl;
+        p.state[ia + a] = make_uint2(pp | (nfl << 15), tt);
+      }
+      {
+        // raw counters of upstream wrappers/metrics.py (kept in registers across the steps of a launch)
+        const int mstep = m_acc2;
+        const int solved_sum = m_acc0 + c_was;
+        const int time_sum = m_acc1 + c_was * mstep;
+        if (done) {
+          if (tid == 0) {
+            int4* last = reinterpret_cast<int4*>(p.metric_last + 4 * (long long)n);
+            *last = make_int4(solved_sum, time_sum + (A - solved_sum) * mstep, mstep + 1, c_was);
+          }
+          m_acc0 = 0;
+          m_acc1 = 0;
+          m_acc2 = 0;
+        } else {
+          m_acc0 = solved_sum;
+          m_acc1 = time_sum;
+          m_acc2 = mstep + 1;
+        }
+        step_idx = do_reset ? 0 : step_idx + 1;
+        if (tid == 0) {
+          p.elapsed[n] = step_idx;
+          p.episode_done[n] = done ? 1 : 0;
+          *reinterpret_cast<int4*>(p.metric_acc + 4 * (long long)n) = make_int4(m_acc0, m_acc1, m_acc2, 0);
         }
       }
-      p.rewards[ia + a] = rew;
-      p.terminated[ia + a] = term;
-      p.truncated[ia + a] = trunc ? 1 : 0;
-      p.was_on_goal[ia + a] = (uint8_t)was;
-      uint32_t pp = s_npos[a];
-      if (do_reset) {
-        const uint2 w = p.state0[ia + a];
-        pp = st_pos(w.x);
-        tt = w.y;
-        nfl = 1u;
-        if (ONTGT == 2) p.rng[ia + a] = p.rng0[ia + a];
-      }
-      s_npos[a] = pp;
-      s_tgt[a] = tt;
-      s_flag[a] = (uint8_t)nfl;
-      p.state[ia + a] = make_uint2(pp | (nfl << 15), tt);
-    }
-    if (tid == 0) {
-      p.elapsed[n] = do_reset ? 0 : step_idx + 1;
-      p.episode_done[n] = done ? 1 : 0;
-      // raw counters of upstream wrappers/metrics.py
-      const int mstep = m_acc2;
-      const int solved_sum = m_acc0 + c_was;
-      const int time_sum = m_acc1 + c_was * mstep;
-      int4* acc = reinterpret_cast<int4*>(p.metric_acc + 4 * (long long)n);
-      if (done) {
-        int4* last = reinterpret_cast<int4*>(p.metric_last + 4 * (long long)n);
-        *last = make_int4(solved_sum, time_sum + (A - solved_sum) * mstep, mstep + 1, c_was);
-        *acc = make_int4(0, 0, 0, 0);
-      } else {
-        *acc = make_int4(solved_sum, time_sum, mstep + 1, 0);
-      }
-    }
-  } else {
-    if (OP == OP_RESET) {
+    } else if (OP == OP_RESET) {
       for (int a = tid; a < A; a += TEAM) {
         p.state[ia + a] = make_uint2(s_pos[a] | 0x8000u, s_tgt[a]);
         p.was_on_goal[ia + a] = (s_pos[a] == s_tgt[a]) ? 1 : 0;
@@ -676,21 +708,22 @@ __global__ void __launch_bounds__(1024, 1)
         *reinterpret_cast<int4*>(p.metric_acc + 4 * (long long)n) = make_int4(0, 0, 0, 0);
       }
     }
-    mbar_wait(s_bar, 0);
-  }
-  PGM_STAMP(5);
-  if (p.obs == nullptr) return;
-  // ---- phase 4: post-move agent bitmap -------------------------------------
-  for (int a = tid; a < A; a += TEAM) {
-    if (s_flag[a] & 1u) {
-      const uint32_t pp = s_npos[a];
-      const int x = pp & 0xFFFF, y = pp >> 16;
-      atomicOr(&s_abits[x * WPR + (y >> 5)], 1u << (y & 31));
+    PGM_STAMP(5);
+    if (obs_k != nullptr) {
+      // ---- phase 4: post-move agent bitmap -------------------------------------
+      for (int a = tid; a < A; a += TEAM) {
+        if (s_flag[a] & 1u) {
+          const uint32_t pp = s_npos[a];
+          const int x = pp & 0xFFFF, y = pp >> 16;
+          atomicOr(&s_abits[x * WPR + (y >> 5)], 1u << (y & 31));
+        }
+      }
+      // (emit_observations starts with stage zeroing + team_sync, which also orders the atomics)
+      // ---- phase 5/6: observation bits, expansion, stores -------------------------
+      emit_observations<TEAM, RT>(p, obs_k, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
     }
+    if (k + 1 < num_steps) team_sync<TEAM>(bar_id);  // stage (aliasing occ) and s_act are rewritten next
   }
-  // (emit_observations starts with stage zeroing + team_sync, which also orders the atomics)
-  // ---- phase 5: observations -------------------------------------------------
-  emit_observations<TEAM, RT>(p, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
 }
 
 }  // namespace pgm

@@ -114,6 +114,12 @@ class Engine:
                                     C.c_void_p(rewards_ptr), C.c_void_p(terminated_ptr),
                                     C.c_void_p(truncated_ptr), C.c_void_p(stream)))
 
+    def step_many(self, num_steps: int, actions_ptr: int, itemsize: int, obs_ptr: int, obs_ring: int,
+                  rewards_ptr: int, terminated_ptr: int, truncated_ptr: int, stream: int = 0):
+        nat.check(self.lib.pgm_step_many(self.handle, num_steps, C.c_void_p(actions_ptr), itemsize,
+                                         C.c_void_p(obs_ptr), obs_ring, C.c_void_p(rewards_ptr),
+                                         C.c_void_p(terminated_ptr), C.c_void_p(truncated_ptr), C.c_void_p(stream)))
+
     # -- host buffer API --------------------------------------------------------- #
     def obs_shape(self):
         if self.obs_format == "bits":

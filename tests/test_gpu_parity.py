@@ -109,3 +109,38 @@ def test_block_both_many_agents():
     gc = dict(size=48, density=0.2, num_agents=600, obs_radius=5, max_episode_steps=32,
               collision_system="block_both", on_target="finish")
     compare(gc, seeds=[3], T=24)
+
+
+@pytest.mark.parametrize("coll,ot", list(itertools.product(COLLISIONS, ON_TARGETS)))
+def test_multi_step_launch_equals_single_steps(coll, ot):
+    """pgm_step_many (K steps in one launch) == K pgm_step launches == the oracle."""
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    gc = dict(size=10, density=0.15, num_agents=24, obs_radius=3, max_episode_steps=9, collision_system=coll,
+              on_target=ot)
+    seeds = list(range(30, 40))
+    K = 25
+    actions = make_actions(K, len(seeds), gc["num_agents"], seed=11)
+    a = BatchedPogema(GridConfig(**gc), num_envs=len(seeds), seeds=seeds, auto_reset=True)
+    b = BatchedPogema(GridConfig(**gc), num_envs=len(seeds), seeds=seeds, auto_reset=True)
+    a.reset(), b.reset()
+    act = torch.from_numpy(actions).cuda()
+    obs, rew, term, trunc = a.rollout(act)
+    for k in range(K):
+        o, r, te, tr = b.step(act[k])
+        assert torch.equal(obs[k], o), k
+        assert torch.equal(rew[k], r) and torch.equal(term[k], te) and torch.equal(trunc[k], tr), k
+    assert torch.equal(a._state(), b._state())
+    assert torch.equal(a.elapsed_steps, b.elapsed_steps)
+    assert np.array_equal(a.engine.get_state(7), b.engine.get_state(7))       # metric counters
+    for i, seed in enumerate(seeds[:4]):
+        ref = run_oracle(gc, seed, actions[:, i], auto_reset=True)
+        assert np.array_equal(obs[:, i].cpu().numpy(), ref["obs"][1:])
+        assert np.array_equal(rew[:, i].cpu().numpy(), ref["rewards"])
+    # observation ring smaller than K: slot k % R holds the last step written to it
+    c = BatchedPogema(GridConfig(**gc), num_envs=len(seeds), seeds=seeds, auto_reset=True)
+    c.reset()
+    ring = torch.empty((4,) + tuple(obs.shape[1:]), dtype=obs.dtype, device="cuda")
+    c.rollout(act, obs_out=ring)
+    for k in range(K - 4, K):
+        assert torch.equal(ring[k % 4], obs[k])

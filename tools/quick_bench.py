@@ -16,6 +16,7 @@ ap.add_argument("--steps", type=int, default=128)
 ap.add_argument("--fmt", default="u8")
 ap.add_argument("--noobs", action="store_true")
 ap.add_argument("--graph", type=int, default=0)
+ap.add_argument("--many", type=int, default=0, help="steps per launch (pgm_step_many)")
 a = ap.parse_args()
 gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, max_episode_steps=64,
                 collision_system=a.coll, on_target=a.ot)
@@ -29,7 +30,20 @@ for i in range(20):
     env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-if a.graph:
+if a.many:
+    K = a.many
+    act_k = torch.stack([acts[i % 16] for i in range(K)])
+    ring = torch.stack(bufs)
+    for _ in range(3):
+        env.rollout(act_k, obs_out=ring, compute_obs=not a.noobs)
+    torch.cuda.synchronize()
+    reps = max(1, a.steps // K)
+    a.steps = reps * K
+    e0.record()
+    for _ in range(reps):
+        env.rollout(act_k, obs_out=ring, compute_obs=not a.noobs)
+    e1.record()
+elif a.graph:
     g = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
