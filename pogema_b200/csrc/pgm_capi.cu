@@ -90,17 +90,6 @@ namespace {
 int compute_plan(pgm_engine* e) {
   const pgm_config& c = e->cfg;
   const int A = c.num_agents;
-  int team = c.team_threads;
-  if (team == 0) {
-    // keep every instance co-resident when possible: ~1024 threads per SM
-    const int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;
-    team = pow2_floor(std::max(32, 1024 / std::max(1, per_sm)));
-    team = std::min(team, std::max(32, pow2_ceil(A)));
-    team = std::min(team, 1024);
-  }
-  if (team != 32 && team != 64 && team != 128 && team != 256 && team != 512 && team != 1024)
-    return fail(PGM_ERR_INVALID, "team_threads must be 0 or a power of two in [32,1024], got %d", team);
-  e->team = team;
   const int occ_bytes = round_up(e->PH * e->PW * 2 + 4, 16);
   const int fixed = e->obst_stride * 4 + round_up((e->PH * e->WPR + 1) * 4, 16) + 4 * round_up(A * 4, 16) +
                     2 * round_up(A, 16) + 16;
@@ -143,14 +132,44 @@ int compute_plan(pgm_engine* e) {
   L.team_smem = round_up(off, 16);
   if (L.team_smem > smem_max)
     return fail(PGM_ERR_UNSUPPORTED, "instance needs %d bytes of shared memory (max %d)", L.team_smem, smem_max);
-  // teams per CTA: about a quarter of the teams an SM hosts (four CTAs per SM)
-  const int per_sm_teams = (c.num_envs + e->sm_count - 1) / e->sm_count;
-  int tpc = std::max(1, std::min(16, (per_sm_teams + 3) / 4));
-  tpc = std::max(tpc, std::min(4, 128 / team));
-  if (const char* v = getenv("PGM_TPC")) tpc = std::max(1, atoi(v));  // tuning knob
-  tpc = std::min(tpc, 1024 / team);
-  while (tpc > 1 && tpc * L.team_smem > smem_max) tpc--;
-  if (team > 32) tpc = std::min(tpc, 15);
+  int team = c.team_threads;
+  if (team == 0) {
+    // ~1024 threads per SM (64 registers each) shared by the instances an SM hosts at a time:
+    // as many as the job needs per SM, unless shared memory allows fewer
+    const int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;
+    const int resident = std::max(1, std::min(per_sm, smem_max / L.team_smem));
+    team = pow2_floor(std::max(32, 1024 / resident));
+    team = std::min(team, std::max(32, pow2_ceil(A)));
+    team = std::min(team, 1024);
+  }
+  if (team != 32 && team != 64 && team != 128 && team != 256 && team != 512 && team != 1024)
+    return fail(PGM_ERR_INVALID, "team_threads must be 0 or a power of two in [32,1024], got %d", team);
+  e->team = team;
+  // teams per CTA: balance the busiest SM (CTAs are dealt round-robin, every SM should host the same
+  // number of instances), prefer CTAs of 192..512 threads (measured: smaller CTAs cost ~15 %)
+  int max_tpc = std::min(1024 / team, std::max(1, smem_max / L.team_smem));
+  if (team > 32) max_tpc = std::min(max_tpc, 15);
+  int tpc = 1;
+  {
+    double best = -1.0;
+    const double ideal = (double)c.num_envs / e->sm_count;
+    for (int t = 1; t <= max_tpc; ++t) {
+      const int grid = (c.num_envs + t - 1) / t;
+      const int per_sm_ctas = (grid + e->sm_count - 1) / e->sm_count;
+      // CTAs resident at once are limited by shared memory and threads; extra CTAs run as later waves
+      const double busiest = (double)per_sm_ctas * t;
+      double score = ideal / busiest;
+      const int threads = t * team;
+      if (threads < 192) score *= 0.85;
+      if (threads > 512) score *= 0.95;
+      score -= 1e-4 * std::abs(threads - 256) / 256.0;  // tie-break: closest to 256 threads
+      if (score > best) {
+        best = score;
+        tpc = t;
+      }
+    }
+  }
+  if (const char* v = getenv("PGM_TPC")) tpc = std::max(1, std::min(max_tpc, atoi(v)));  // tuning knob
   e->tpc = tpc;
   L.teams_per_cta = tpc;
   e->cta_threads = tpc * team;

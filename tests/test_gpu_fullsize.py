@@ -148,37 +148,7 @@ def test_config2_team_variants_agree():
             assert torch.equal(obs, ref[0]) and torch.equal(rsum, ref[1])
 
 
-def maze_map(size, seed):
-    """Seeded recursive-backtracker maze on a (size/2)^2 cell lattice."""
-    rng = np.random.default_rng(seed)
-    n = size // 2
-    m = np.ones((size, size), np.uint8)
-    seen = np.zeros((n, n), bool)
-    stack = [(0, 0)]
-    seen[0, 0] = True
-    m[0, 0] = 0
-    while stack:
-        x, y = stack[-1]
-        nb = [(x + dx, y + dy) for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1))
-              if 0 <= x + dx < n and 0 <= y + dy < n and not seen[x + dx, y + dy]]
-        if not nb:
-            stack.pop()
-            continue
-        nx, ny = nb[rng.integers(len(nb))]
-        seen[nx, ny] = True
-        m[2 * nx, 2 * ny] = 0
-        m[x + nx, y + ny] = 0
-        stack.append((nx, ny))
-    return m
-
-
-def warehouse_map(size):
-    """Regular 2x8 shelf blocks with one-cell aisles (config 4)."""
-    m = np.zeros((size, size), np.uint8)
-    for x in range(2, size - 2, 3):
-        for y in range(2, size - 9, 10):
-            m[x:x + 2, y:y + 8] = 1
-    return m
+from pogema_b200.maps import maze_map, warehouse_map  # noqa: E402
 
 
 def test_config3_lifelong_maze_soft():

@@ -15,11 +15,15 @@ ap.add_argument("--team", type=int, default=0)
 ap.add_argument("--steps", type=int, default=128)
 ap.add_argument("--fmt", default="u8")
 ap.add_argument("--noobs", action="store_true")
+ap.add_argument("--map", default="random", choices=["random", "maze", "warehouse"])
+ap.add_argument("--max-steps", type=int, default=64)
 ap.add_argument("--graph", type=int, default=0)
 ap.add_argument("--many", type=int, default=0, help="steps per launch (pgm_step_many)")
 a = ap.parse_args()
-gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, max_episode_steps=64,
-                collision_system=a.coll, on_target=a.ot)
+from pogema_b200.maps import maze_map, warehouse_map
+mp = None if a.map == "random" else (maze_map(a.size, 3) if a.map == "maze" else warehouse_map(a.size)).tolist()
+gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, max_episode_steps=a.max_steps,
+                collision_system=a.coll, on_target=a.ot, map=mp)
 t0 = time.time()
 env = BatchedPogema(gc, num_envs=a.n, auto_reset=True, team_threads=a.team, obs_format=a.fmt)
 t_gen = time.time() - t0
