@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(1024, 1)
       s_flag[a1] = (uint8_t)st_active(w1.x);
     }
   }
+  team_sync<TEAM>(bar_id);  // the mbarrier was initialised by thread 0 of the team
   mbar_wait(s_bar, 0);
 
   // One launch advances this instance by p.num_steps steps (1 for pgm_step; >1 for pgm_step_many,
@@ -572,22 +573,28 @@ __global__ void __launch_bounds__(1024, 1)
         s_link[a] = link;
         pend |= ((link & 3u) == ST_PEND);
       }
+      // pointer jumping along occupant chains, double buffered (s_link <-> s_npos, which is free until
+      // phase 3) so that a round only reads what the previous round wrote; what is still pending after
+      // max_rounds is a rotation cycle (soft only) and succeeds
+      uint32_t* link_cur = s_link;
       if (COLL != 1) {
-        // pointer jumping along occupant chains; what is still pending after
-        // max_rounds is a rotation cycle (soft only) and succeeds
+        uint32_t* link_nxt = s_npos;
         int rounds = 0;
         while (team_any<TEAM>(bar_id, pend)) {
           if (++rounds > p.max_rounds) break;
           pend = false;
           for (int a = tid; a < A; a += TEAM) {
-            const uint32_t l = s_link[a];
+            uint32_t l = link_cur[a];
             if ((l & 3u) == ST_PEND) {
-              const uint32_t lp = s_link[l >> 2];
-              const uint32_t nl = ((lp & 3u) == ST_PEND) ? (ST_PEND | (lp & ~3u)) : (lp & 3u);
-              s_link[a] = nl;
-              pend |= ((nl & 3u) == ST_PEND);
+              const uint32_t lp = link_cur[l >> 2];
+              l = ((lp & 3u) == ST_PEND) ? (ST_PEND | (lp & ~3u)) : (lp & 3u);
+              pend |= ((l & 3u) == ST_PEND);
             }
+            link_nxt[a] = l;
           }
+          uint32_t* t = link_cur;
+          link_cur = link_nxt;
+          link_nxt = t;
         }
       }
       team_sync<TEAM>(bar_id);
@@ -598,7 +605,7 @@ __global__ void __launch_bounds__(1024, 1)
       for (int a = tid; a < A; a += TEAM) {
         const uint32_t act = s_act[a];
         uint32_t pp = s_pos[a];
-        if ((s_link[a] & 3u) != ST_FAIL) {
+        if ((link_cur[a] & 3u) != ST_FAIL) {
           const int tx = (int)(pp & 0xFFFF) + move_dx(act), ty = (int)(pp >> 16) + move_dy(act);
           pp = (uint32_t)tx | ((uint32_t)ty << 16);
         }
