@@ -7,9 +7,9 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O3,-Wall
 CSRC := pogema_b200/csrc
 BUILD := build
 LIB := pogema_b200/_lib/libpgm_b200.so
-CU := pgm_capi pgm_inst_step_priority pgm_inst_step_block_both pgm_inst_step_soft pgm_inst_observe pgm_inst_reset
+CU := pgm_capi pgm_devgen pgm_inst_step_priority pgm_inst_step_block_both pgm_inst_step_soft pgm_inst_observe pgm_inst_reset
 OBJS := $(addprefix $(BUILD)/,$(addsuffix .o,$(CU))) $(BUILD)/pgm_gen.o
-HDRS := $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h include/pgm_b200.h
+HDRS := $(CSRC)/pgm_devgen.h $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h include/pgm_b200.h
 
 all: $(LIB) oracle
 

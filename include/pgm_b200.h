@@ -128,6 +128,13 @@ int64_t pgm_obs_instance_stride(const pgm_engine* e);  /* bytes between consecut
 int pgm_generate(pgm_engine* e, int32_t first, int32_t count, const uint64_t* seeds_host,
                  double density, const uint8_t* map_host, int32_t num_threads,
                  int32_t* failed_index, void* stream);
+/* Same result as pgm_generate, built ON THE DEVICE (one warp per instance: PCG64 jump-ahead obstacle
+ * draws, component labelling, shuffle, placing, border, lifelong tables) - three orders of magnitude
+ * faster than the host path, for resets with new seeds.  Instances that need upstream's retry loop
+ * are regenerated by the host generator (*num_host_fallbacks, optional, counts them). */
+int pgm_generate_device(pgm_engine* e, int32_t first, int32_t count, const uint64_t* seeds_host,
+                        double density, const uint8_t* map_host, int32_t* num_host_fallbacks,
+                        void* stream);
 int pgm_set_tasks(pgm_engine* e, int32_t first, int32_t count, const uint8_t* obstacles_host,
                   const int32_t* agents_xy_host, const int32_t* targets_xy_host,
                   const uint64_t* seeds_host, void* stream);

@@ -22,7 +22,7 @@ STATE_POSITIONS, STATE_TARGETS, STATE_ACTIVE, STATE_ELAPSED, STATE_OBSTACLES, ST
 # every symbol include/pgm_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
     "pgm_last_error", "pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_obs_bytes",
-    "pgm_obs_instance_stride", "pgm_generate", "pgm_generate_host", "pgm_set_tasks", "pgm_reset", "pgm_observe", "pgm_step",
+    "pgm_obs_instance_stride", "pgm_generate", "pgm_generate_device", "pgm_generate_host", "pgm_set_tasks", "pgm_reset", "pgm_observe", "pgm_step",
     "pgm_step_many", "pgm_step_host", "pgm_observe_host", "pgm_get_state", "pgm_state_ptr", "pgm_checkpoint_bytes", "pgm_checkpoint_save",
     "pgm_checkpoint_load", "pgm_check_errors", "pgm_launch_count", "pgm_plan", "pgm_set_debug_buffer",
 ]
@@ -64,6 +64,7 @@ def load():
     lib.pgm_obs_instance_stride.argtypes = [vp]
     lib.pgm_obs_instance_stride.restype = i64
     lib.pgm_generate.argtypes = [vp, i32, i32, vp, C.c_double, vp, i32, C.POINTER(i32), vp]
+    lib.pgm_generate_device.argtypes = [vp, i32, i32, vp, C.c_double, vp, C.POINTER(i32), vp]
     lib.pgm_generate_host.argtypes = [i32, i32, i32, i32, C.c_double, i32, vp, C.c_uint64, vp, vp, vp, vp, vp]
     lib.pgm_set_tasks.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.pgm_reset.argtypes = [vp, vp, vp]

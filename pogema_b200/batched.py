@@ -42,7 +42,7 @@ class BatchedPogema:
 
     def __init__(self, grid_config: Optional[GridConfig] = None, num_envs: int = 1, device="cuda",
                  seeds: Optional[Sequence[int]] = None, auto_reset: bool = True, obs_format: str = "u8",
-                 team_threads: int = 0, num_threads: int = 0, **kwargs):
+                 team_threads: int = 0, num_threads: int = 0, generate_on_device: bool = True, **kwargs):
         if grid_config is None:
             grid_config = GridConfig(**kwargs)
         elif isinstance(grid_config, dict):
@@ -65,7 +65,9 @@ class BatchedPogema:
             seeds = np.arange(base, base + self.num_envs, dtype=np.uint64)
         self.seeds = np.asarray(seeds, dtype=np.uint64)
         assert len(self.seeds) == self.num_envs
-        self.engine.generate(self.seeds, num_threads=num_threads, stream=self._stream())
+        self.generate_on_device = bool(generate_on_device) and grid_config.agents_xy is None
+        self.engine.generate(self.seeds, num_threads=num_threads, stream=self._stream(),
+                             on_device=self.generate_on_device)
         n, a = self.num_envs, self.num_agents
         with torch.cuda.device(self.device):
             self._obs = self._alloc_obs()
@@ -87,8 +89,15 @@ class BatchedPogema:
         return self._alloc_obs()
 
     # ------------------------------------------------------------------ #
-    def reset(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def reset(self, out: Optional[torch.Tensor] = None, seeds: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """Restore every instance to its initial task (upstream: same seed -> same map/task).  With
+        ``seeds`` the instances are REBUILT for the new seeds by the device-side generator
+        (``pgm_generate_device``), i.e. ``pogema_v0(GridConfig(seed=seeds[k])).reset()`` for every k."""
         obs = self._obs if out is None else out
+        if seeds is not None:
+            self.seeds = np.asarray(seeds, dtype=np.uint64)
+            assert len(self.seeds) == self.num_envs
+            self.engine.generate(self.seeds, stream=self._stream(), on_device=self.generate_on_device)
         self.engine.reset(obs.data_ptr(), self._stream())
         return obs
 

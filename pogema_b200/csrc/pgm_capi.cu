@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/pgm_b200.h"
+#include "pgm_devgen.h"
 #include "pgm_gen.h"
 #include "pgm_launch.cuh"
 
@@ -81,6 +82,14 @@ struct pgm_engine {
   int act_h_itemsize = 0;
   // host mirrors
   std::vector<uint32_t> h_obst;
+  bool h_obst_valid = true;  // false after a device-side generation (obstacles are read back on demand)
+  // device generator buffers
+  uint64_t* d_gen_seeds = nullptr;
+  int* d_gen_fail = nullptr;
+  int* d_gen_index = nullptr;
+  uint8_t* d_gen_map = nullptr;
+  int* d_gen_scratch = nullptr;
+  long long gen_scratch_bytes = 0;
   int64_t launches = 0;
   bool use_pdl = true;
 };
@@ -434,7 +443,7 @@ int pgm_destroy(pgm_engine* e) {
   void* ptrs[] = {e->d_obst,  e->d_state, e->d_state0, e->d_was,
                   e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
                   e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h, e->d_term_h, e->d_trunc_h,
-                  e->d_rew_h};
+                  e->d_rew_h, e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -526,6 +535,91 @@ int pgm_generate_host(int32_t height, int32_t width, int32_t num_agents, int32_t
     }
     if (gp.lifelong && comp_size_out) comp_size_out[a] = inst.comp_size[a];
   }
+  return PGM_OK;
+}
+
+int pgm_generate_device(pgm_engine* e, int32_t first, int32_t count, const uint64_t* seeds, double density,
+                        const uint8_t* map_host, int32_t* num_host_fallbacks, void* stream) {
+  if (!e || !seeds) return fail(PGM_ERR_INVALID, "null argument");
+  if (first < 0 || count < 0 || first + count > e->cfg.num_envs) return fail(PGM_ERR_INVALID, "bad instance range");
+  if (!(density >= 0.0 && density <= 1.0)) return fail(PGM_ERR_INVALID, "density must be in [0,1]");
+  if (num_host_fallbacks) *num_host_fallbacks = 0;
+  if (count == 0) return PGM_OK;
+  DeviceGuard guard(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = e->cfg.num_envs, A = e->cfg.num_agents, HW = e->cfg.height * e->cfg.width;
+  if (!e->d_gen_seeds) {
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_seeds, (size_t)N * 8));
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_fail, (size_t)N * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_index, (size_t)N * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_map, (size_t)HW));
+  }
+  const long long per_inst = devgen_scratch_bytes(HW, A, 1);
+  const int chunk = (int)std::max<long long>(1, std::min<long long>(count, (256LL << 20) / per_inst));
+  if (e->gen_scratch_bytes < per_inst * chunk) {
+    if (e->d_gen_scratch) cudaFree(e->d_gen_scratch);
+    e->d_gen_scratch = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_scratch, (size_t)(per_inst * chunk)));
+    e->gen_scratch_bytes = per_inst * chunk;
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->d_gen_seeds, seeds, (size_t)count * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(e->d_gen_fail, 0, (size_t)count * 4, s));
+  if (map_host) CUDA_TRY(cudaMemcpyAsync(e->d_gen_map, map_host, (size_t)HW, cudaMemcpyHostToDevice, s));
+  DevGenArgs a{};
+  a.index = nullptr;
+  a.H = e->cfg.height;
+  a.W = e->cfg.width;
+  a.A = A;
+  a.r = e->cfg.obs_radius;
+  a.lifelong = e->lifelong ? 1 : 0;
+  a.map = map_host ? e->d_gen_map : nullptr;
+  binomial1_constants(density, &a.binom_zero, &a.binom_flip, &a.binom_qn, &a.binom_px1);
+  a.scratch = e->d_gen_scratch;
+  a.obst = e->d_obst;
+  a.obst_stride = e->obst_stride;
+  a.state = e->d_state;
+  a.state0 = e->d_state0;
+  a.elapsed = e->d_elapsed;
+  a.episode_done = e->d_done;
+  a.was_on_goal = e->d_was;
+  a.metric_acc = e->d_macc;
+  a.metric_last = e->d_mlast;
+  a.rng = e->d_rng;
+  a.rng0 = e->d_rng0;
+  a.comp_start = e->d_cstart;
+  a.comp_size = e->d_csize;
+  a.cells = e->d_cells;
+  a.cells_stride = e->cells_stride;
+  for (int off = 0; off < count; off += chunk) {
+    a.first = first + off;
+    a.count = std::min(chunk, count - off);
+    a.seeds = e->d_gen_seeds + off;
+    a.fail = e->d_gen_fail + off;
+    int err = launch_devgen(a, s);
+    if (err != 0) return fail(PGM_ERR_CUDA, "device generator launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    e->launches++;
+  }
+  std::vector<int> failed(count);
+  CUDA_TRY(cudaMemcpyAsync(failed.data(), e->d_gen_fail, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  e->h_obst_valid = false;
+  e->tasks_ready = true;
+  // the rare instances that need upstream's retry loop (or raise OverflowError) go through the host generator
+  GenParams gp = gen_params(e, density, map_host);
+  int nfb = 0;
+  for (int k = 0; k < count; ++k) {
+    if (!failed[k]) continue;
+    std::vector<GenInstance> one(1);
+    if (generate_instance(gp, seeds[k], one[0]) != 0)
+      return fail(PGM_ERR_OVERFLOW,
+                  "Can't create task. Please check grid grid_config, especially density, num_agent and map. "
+                  "(instance %d, seed %llu)",
+                  first + k, (unsigned long long)seeds[k]);
+    int rc = upload_instances(e, first + k, 1, one, s);
+    if (rc != PGM_OK) return rc;
+    nfb++;
+  }
+  if (num_host_fallbacks) *num_host_fallbacks = nfb;
   return PGM_OK;
 }
 
@@ -699,6 +793,11 @@ int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, voi
     case PGM_STATE_OBSTACLES: {
       const int64_t H = e->cfg.height, W = e->cfg.width;
       if (need(N * H * W)) return PGM_ERR_INVALID;
+      if (!e->h_obst_valid) {
+        CUDA_TRY(cudaMemcpyAsync(e->h_obst.data(), e->d_obst, e->h_obst.size() * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        e->h_obst_valid = true;
+      }
       uint8_t* o = (uint8_t*)dst;
       for (int64_t n = 0; n < N; ++n) {
         const uint32_t* bits = &e->h_obst[(size_t)n * e->obst_stride];

@@ -1,0 +1,42 @@
+// pgm_devgen.h - device-side task generation (see pgm_devgen.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pgm_rng.h"
+
+namespace pgm {
+
+struct DevGenArgs {
+  int first, count;        // instances [first, first+count) unless `index` is given
+  const int* index;        // optional device array [count] of instance indices
+  const uint64_t* seeds;   // device [count]
+  int H, W, A, r, lifelong;
+  const uint8_t* map;      // optional device map [H][W] shared by all instances
+  // numpy random_binomial(p, n=1) constants computed on the host (libm exp/log)
+  int binom_zero, binom_flip;
+  double binom_qn, binom_px1;
+  int* scratch;            // devgen_scratch_bytes(...)
+  int* fail;               // device [count], zero on entry; != 0 -> regenerate on the host
+  // engine arrays
+  uint32_t* obst;
+  int obst_stride;
+  uint2* state;
+  uint2* state0;
+  int32_t* elapsed;
+  uint8_t* episode_done;
+  uint8_t* was_on_goal;
+  int32_t* metric_acc;
+  int32_t* metric_last;
+  Pcg64* rng;
+  Pcg64* rng0;
+  int32_t* comp_start;
+  int32_t* comp_size;
+  uint32_t* cells;
+  long long cells_stride;
+};
+
+long long devgen_scratch_bytes(int HW, int A, int count);
+int launch_devgen(const DevGenArgs& a, cudaStream_t s);  // returns a cudaError_t
+
+}  // namespace pgm

@@ -239,6 +239,14 @@ void finish_instance(const GenParams& p, uint64_t seed, const std::vector<uint8_
 
 }  // namespace
 
+void binomial1_constants(double p, int* zero, int* flip, double* qn, double* px1) {
+  Binomial1 b(p);
+  *zero = b.zero ? 1 : 0;
+  *flip = b.flip ? 1 : 0;
+  *qn = b.qn;
+  *px1 = b.zero ? 0.0 : ((1 - 1 + 1) * b.pe * b.qn) / (1 * b.q);
+}
+
 int generate_instance(const GenParams& p, uint64_t seed, GenInstance& out) {
   Pcg64 grid_rnd;  // Grid.rnd = default_rng(seed)
   pcg64_seed(grid_rnd, seed);

@@ -32,6 +32,10 @@ struct GenInstance {
   std::vector<uint32_t> cells;          // packed padded coords, grouped by component, row-major inside
 };
 
+// Constants of numpy's random_binomial(p, n=1) inversion draw, computed with the host libm exactly as
+// numpy does: a cell is an obstacle iff (U > qn) [xor flip]; px1 is the next inversion threshold.
+void binomial1_constants(double p, int* zero, int* flip, double* qn, double* px1);
+
 // Returns 0, or -1 for the upstream OverflowError ("Can't create task").
 int generate_instance(const GenParams& p, uint64_t seed, GenInstance& out);
 

@@ -64,7 +64,8 @@ class Engine:
             pass
 
     # -- task construction -------------------------------------------------- #
-    def generate(self, seeds: Sequence[int], first: int = 0, num_threads: int = 0, stream: int = 0):
+    def generate(self, seeds: Sequence[int], first: int = 0, num_threads: int = 0, stream: int = 0,
+                 on_device: bool = False):
         """upstream Grid.__init__ for instances [first, first+len(seeds)) (see pgm_generate)."""
         gc = self.grid_config
         seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
@@ -87,6 +88,12 @@ class Engine:
                                              _ptr(seeds), C.c_void_p(stream)))
             return
         m = gc.map_array()
+        if on_device:
+            nfb = C.c_int32(0)
+            nat.check(self.lib.pgm_generate_device(self.handle, first, len(seeds), _ptr(seeds), float(gc.density),
+                                                   _ptr(m), C.byref(nfb), C.c_void_p(stream)))
+            self.last_host_fallbacks = int(nfb.value)
+            return
         nat.check(self.lib.pgm_generate(self.handle, first, len(seeds), _ptr(seeds), float(gc.density),
                                         _ptr(m), num_threads, C.byref(failed), C.c_void_p(stream)))
 
