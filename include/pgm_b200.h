@@ -85,10 +85,15 @@ typedef struct pgm_config {
   int32_t auto_reset;        /* 1: an instance whose episode ended is restored to its
                                 initial state inside the same step and the returned
                                 observation is the reset one (upstream
-                                integrations/sample_factory.py :: AutoResetWrapper)  */
+                                integrations/sample_factory.py :: AutoResetWrapper).
+                                2: instead of restoring the same task, the instance is
+                                REBUILT on the device from its next seed
+                                (seed += reserved[0] or num_envs) right after the step -
+                                upstream's behaviour with a changing seed (seed=None
+                                draws a fresh map on every reset)                     */
   int32_t obs_format;        /* PGM_OBS_*                                            */
   int32_t team_threads;      /* threads cooperating on one instance; 0 = choose      */
-  int32_t reserved[3];
+  int32_t reserved[3];       /* [0]: seed stride of auto_reset=2 (0 = num_envs)         */
 } pgm_config;
 
 typedef struct pgm_engine pgm_engine;

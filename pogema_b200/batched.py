@@ -38,11 +38,15 @@ class BatchedPogema:
     instance whose episode ended (all terminated or all truncated) is restored to
     its initial task inside the same step and ``obs`` holds the reset observation
     (upstream integrations/sample_factory.py :: AutoResetWrapper semantics).
+    ``auto_reset="reseed"`` rebuilds such an instance on the device from a NEW seed
+    instead (``seed += reseed_stride``, default ``num_envs``): a fresh random map and
+    task for every episode, exactly ``pogema_v0(GridConfig(seed=new_seed)).reset()``.
     """
 
     def __init__(self, grid_config: Optional[GridConfig] = None, num_envs: int = 1, device="cuda",
-                 seeds: Optional[Sequence[int]] = None, auto_reset: bool = True, obs_format: str = "u8",
-                 team_threads: int = 0, num_threads: int = 0, generate_on_device: bool = True, **kwargs):
+                 seeds: Optional[Sequence[int]] = None, auto_reset=True, obs_format: str = "u8",
+                 team_threads: int = 0, num_threads: int = 0, generate_on_device: bool = True,
+                 reseed_stride: int = 0, **kwargs):
         if grid_config is None:
             grid_config = GridConfig(**kwargs)
         elif isinstance(grid_config, dict):
@@ -57,9 +61,9 @@ class BatchedPogema:
         self.grid_config = grid_config
         self.num_envs = int(num_envs)
         self.num_agents = int(grid_config.num_agents)
-        self.auto_reset = bool(auto_reset)
+        self.auto_reset = auto_reset
         self.engine = Engine(grid_config, num_envs, device=dev_index, auto_reset=auto_reset,
-                             obs_format=obs_format, team_threads=team_threads)
+                             obs_format=obs_format, team_threads=team_threads, reseed_stride=reseed_stride)
         if seeds is None:
             base = grid_config.seed or 0
             seeds = np.arange(base, base + self.num_envs, dtype=np.uint64)

@@ -90,6 +90,14 @@ struct pgm_engine {
   uint8_t* d_gen_map = nullptr;
   int* d_gen_scratch = nullptr;
   long long gen_scratch_bytes = 0;
+  // auto_reset == 2 (rebuild the task from a new seed when an episode ends)
+  uint64_t* d_cur_seeds = nullptr;
+  uint8_t* d_regen_flag = nullptr;
+  int* d_regen_count = nullptr;
+  double gen_density = -1.0;  // parameters of the last pgm_generate*, reused by the rebuilds
+  bool gen_has_map = false;
+  bool gen_explicit = false;
+  int regen_slots = 0;
   int64_t launches = 0;
   bool use_pdl = true;
 };
@@ -252,6 +260,8 @@ StepArgs make_args(pgm_engine* e) {
   a.truncated = nullptr;
   a.err_flag = e->d_err;
   a.debug = e->d_debug;
+  a.regen_flag = e->d_regen_flag;
+  a.mask = nullptr;
   return a;
 }
 
@@ -354,6 +364,108 @@ int ensure_host_scratch(pgm_engine* e, int itemsize) {
   return PGM_OK;
 }
 
+int ensure_gen_buffers(pgm_engine* e, int slots_wanted) {
+  const int N = e->cfg.num_envs, A = e->cfg.num_agents, HW = e->cfg.height * e->cfg.width;
+  if (!e->d_gen_seeds) {
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_seeds, (size_t)N * 8));
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_fail, (size_t)N * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_index, (size_t)N * 4));
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_map, (size_t)HW));
+  }
+  const long long per_inst = devgen_scratch_bytes(HW, A, 1);
+  const int slots = (int)std::max<long long>(1, std::min<long long>(slots_wanted, (256LL << 20) / per_inst));
+  if (e->gen_scratch_bytes < per_inst * slots) {
+    if (e->d_gen_scratch) cudaFree(e->d_gen_scratch);
+    e->d_gen_scratch = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&e->d_gen_scratch, (size_t)(per_inst * slots)));
+    e->gen_scratch_bytes = per_inst * slots;
+  }
+  return slots;
+}
+
+// remember how the tasks were generated (rebuilds with new seeds reuse it) and the current seeds
+int remember_generation(pgm_engine* e, int first, int count, const uint64_t* seeds, double density,
+                        const uint8_t* map_host, bool explicit_tasks, cudaStream_t s) {
+  e->gen_density = density;
+  e->gen_has_map = map_host != nullptr;
+  e->gen_explicit = explicit_tasks;
+  if (seeds) CUDA_TRY(cudaMemcpyAsync(e->d_cur_seeds + first, seeds, (size_t)count * 8, cudaMemcpyHostToDevice, s));
+  if (map_host) {
+    int rc = ensure_gen_buffers(e, 1);
+    if (rc < 0) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->d_gen_map, map_host, (size_t)e->cfg.height * e->cfg.width, cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return PGM_OK;
+}
+
+DevGenArgs devgen_args(pgm_engine* e, double density, bool has_map) {
+  DevGenArgs a{};
+  a.H = e->cfg.height;
+  a.W = e->cfg.width;
+  a.A = e->cfg.num_agents;
+  a.r = e->cfg.obs_radius;
+  a.lifelong = e->lifelong ? 1 : 0;
+  a.map = has_map ? e->d_gen_map : nullptr;
+  binomial1_constants(density, &a.binom_zero, &a.binom_flip, &a.binom_qn, &a.binom_px1);
+  a.scratch = e->d_gen_scratch;
+  a.err_flag = e->d_err;
+  a.obst = e->d_obst;
+  a.obst_stride = e->obst_stride;
+  a.state = e->d_state;
+  a.state0 = e->d_state0;
+  a.elapsed = e->d_elapsed;
+  a.episode_done = e->d_done;
+  a.was_on_goal = e->d_was;
+  a.metric_acc = e->d_macc;
+  a.metric_last = e->d_mlast;
+  a.rng = e->d_rng;
+  a.rng0 = e->d_rng0;
+  a.comp_start = e->d_cstart;
+  a.comp_size = e->d_csize;
+  a.cells = e->d_cells;
+  a.cells_stride = e->cells_stride;
+  return a;
+}
+
+// auto_reset == 2: after a step, rebuild every instance whose episode ended from its next seed
+// (compact the flags -> device generator over the list -> masked observe pass)
+int enqueue_rebuilds(pgm_engine* e, void* obs_dev, cudaStream_t s) {
+  if (e->gen_density < 0.0 || e->gen_explicit)
+    return fail(PGM_ERR_STATE, "auto_reset=2 needs tasks built by pgm_generate / pgm_generate_device");
+  if (e->regen_slots == 0) {
+    int slots = ensure_gen_buffers(e, e->cfg.num_envs);
+    if (slots < 0) return slots;
+    e->regen_slots = slots;
+  }
+  const uint64_t stride = e->cfg.reserved[0] > 0 ? (uint64_t)e->cfg.reserved[0] : (uint64_t)e->cfg.num_envs;
+  CUDA_TRY(cudaMemsetAsync(e->d_regen_count, 0, sizeof(int), s));
+  int err = launch_regen_compact(e->cfg.num_envs, e->d_regen_flag, e->d_cur_seeds, stride, e->d_gen_index,
+                                 e->d_regen_count, s);
+  if (err != 0) return fail(PGM_ERR_CUDA, "regen compact launch failed: %s", cudaGetErrorString((cudaError_t)err));
+  DevGenArgs a = devgen_args(e, e->gen_density, e->gen_has_map);
+  a.first = 0;
+  a.count = 0;
+  a.index = e->d_gen_index;
+  a.count_ptr = e->d_regen_count;
+  a.seeds = nullptr;
+  a.cur_seeds = e->d_cur_seeds;
+  a.fail = nullptr;
+  a.slots = e->regen_slots;
+  err = launch_devgen(a, s);
+  if (err != 0) return fail(PGM_ERR_CUDA, "device generator launch failed: %s", cudaGetErrorString((cudaError_t)err));
+  e->launches += 2;
+  e->h_obst_valid = false;
+  if (obs_dev) {
+    StepArgs o = make_args(e);
+    o.obs = (uint8_t*)obs_dev;
+    o.mask = e->d_regen_flag;
+    return launch(e, o, OP_OBSERVE, s);
+  }
+  CUDA_TRY(cudaMemsetAsync(e->d_regen_flag, 0, (size_t)e->cfg.num_envs, s));
+  return PGM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -375,6 +487,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
   if (cfg->max_episode_steps < 1) return fail(PGM_ERR_INVALID, "max_episode_steps must be >= 1");
   if (cfg->collision_system < 0 || cfg->collision_system > 2) return fail(PGM_ERR_INVALID, "bad collision_system");
   if (cfg->on_target < 0 || cfg->on_target > 2) return fail(PGM_ERR_INVALID, "bad on_target");
+  if (cfg->auto_reset < 0 || cfg->auto_reset > 2) return fail(PGM_ERR_INVALID, "auto_reset must be 0, 1 or 2");
   if (cfg->obs_format < 0 || cfg->obs_format > 1) return fail(PGM_ERR_INVALID, "bad obs_format");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -424,6 +537,9 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
   TRY_ALLOC(dev_alloc(&e->d_macc, (size_t)N * 4));
   TRY_ALLOC(dev_alloc(&e->d_mlast, (size_t)N * 4));
   TRY_ALLOC(dev_alloc(&e->d_err, 1));
+  TRY_ALLOC(dev_alloc(&e->d_cur_seeds, (size_t)N));
+  TRY_ALLOC(dev_alloc(&e->d_regen_flag, (size_t)N));
+  TRY_ALLOC(dev_alloc(&e->d_regen_count, 1));
   if (e->lifelong) {
     TRY_ALLOC(dev_alloc(&e->d_rng, (size_t)N * A));
     TRY_ALLOC(dev_alloc(&e->d_rng0, (size_t)N * A));
@@ -443,7 +559,7 @@ int pgm_destroy(pgm_engine* e) {
   void* ptrs[] = {e->d_obst,  e->d_state, e->d_state0, e->d_was,
                   e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
                   e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h, e->d_term_h, e->d_trunc_h,
-                  e->d_rew_h, e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch};
+                  e->d_rew_h, e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -496,6 +612,10 @@ int pgm_generate(pgm_engine* e, int32_t first, int32_t count, const uint64_t* se
                 "(instance %d, seed %llu)",
                 first + bad.load(), (unsigned long long)seeds[bad.load()]);
   }
+  {
+    int rc = remember_generation(e, first, count, seeds, density, map_host, false, (cudaStream_t)stream);
+    if (rc != PGM_OK) return rc;
+  }
   return upload_instances(e, first, count, inst, (cudaStream_t)stream);
 }
 
@@ -547,52 +667,20 @@ int pgm_generate_device(pgm_engine* e, int32_t first, int32_t count, const uint6
   if (count == 0) return PGM_OK;
   DeviceGuard guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
-  const int N = e->cfg.num_envs, A = e->cfg.num_agents, HW = e->cfg.height * e->cfg.width;
-  if (!e->d_gen_seeds) {
-    CUDA_TRY(cudaMalloc((void**)&e->d_gen_seeds, (size_t)N * 8));
-    CUDA_TRY(cudaMalloc((void**)&e->d_gen_fail, (size_t)N * 4));
-    CUDA_TRY(cudaMalloc((void**)&e->d_gen_index, (size_t)N * 4));
-    CUDA_TRY(cudaMalloc((void**)&e->d_gen_map, (size_t)HW));
-  }
-  const long long per_inst = devgen_scratch_bytes(HW, A, 1);
-  const int chunk = (int)std::max<long long>(1, std::min<long long>(count, (256LL << 20) / per_inst));
-  if (e->gen_scratch_bytes < per_inst * chunk) {
-    if (e->d_gen_scratch) cudaFree(e->d_gen_scratch);
-    e->d_gen_scratch = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&e->d_gen_scratch, (size_t)(per_inst * chunk)));
-    e->gen_scratch_bytes = per_inst * chunk;
-  }
+  const int chunk = ensure_gen_buffers(e, count);
+  if (chunk < 0) return chunk;
+  int rc = remember_generation(e, first, count, seeds, density, map_host, false, s);
+  if (rc != PGM_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(e->d_gen_seeds, seeds, (size_t)count * 8, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemsetAsync(e->d_gen_fail, 0, (size_t)count * 4, s));
-  if (map_host) CUDA_TRY(cudaMemcpyAsync(e->d_gen_map, map_host, (size_t)HW, cudaMemcpyHostToDevice, s));
-  DevGenArgs a{};
+  DevGenArgs a = devgen_args(e, density, map_host != nullptr);
   a.index = nullptr;
-  a.H = e->cfg.height;
-  a.W = e->cfg.width;
-  a.A = A;
-  a.r = e->cfg.obs_radius;
-  a.lifelong = e->lifelong ? 1 : 0;
-  a.map = map_host ? e->d_gen_map : nullptr;
-  binomial1_constants(density, &a.binom_zero, &a.binom_flip, &a.binom_qn, &a.binom_px1);
-  a.scratch = e->d_gen_scratch;
-  a.obst = e->d_obst;
-  a.obst_stride = e->obst_stride;
-  a.state = e->d_state;
-  a.state0 = e->d_state0;
-  a.elapsed = e->d_elapsed;
-  a.episode_done = e->d_done;
-  a.was_on_goal = e->d_was;
-  a.metric_acc = e->d_macc;
-  a.metric_last = e->d_mlast;
-  a.rng = e->d_rng;
-  a.rng0 = e->d_rng0;
-  a.comp_start = e->d_cstart;
-  a.comp_size = e->d_csize;
-  a.cells = e->d_cells;
-  a.cells_stride = e->cells_stride;
+  a.count_ptr = nullptr;
+  a.cur_seeds = nullptr;
   for (int off = 0; off < count; off += chunk) {
     a.first = first + off;
     a.count = std::min(chunk, count - off);
+    a.slots = a.count;
     a.seeds = e->d_gen_seeds + off;
     a.fail = e->d_gen_fail + off;
     int err = launch_devgen(a, s);
@@ -615,7 +703,7 @@ int pgm_generate_device(pgm_engine* e, int32_t first, int32_t count, const uint6
                   "Can't create task. Please check grid grid_config, especially density, num_agent and map. "
                   "(instance %d, seed %llu)",
                   first + k, (unsigned long long)seeds[k]);
-    int rc = upload_instances(e, first + k, 1, one, s);
+    rc = upload_instances(e, first + k, 1, one, s);
     if (rc != PGM_OK) return rc;
     nfb++;
   }
@@ -637,6 +725,7 @@ int pgm_set_tasks(pgm_engine* e, int32_t first, int32_t count, const uint8_t* ob
                                targets_xy + k * a2, inst[k]);
     if (rc != 0) return fail(PGM_ERR_INVALID, "Position is out of bounds! (instance %d)", first + k);
   }
+  e->gen_explicit = true;
   return upload_instances(e, first, count, inst, (cudaStream_t)stream);
 }
 
@@ -646,6 +735,7 @@ int pgm_reset(pgm_engine* e, void* obs_dev, void* stream) {
   DeviceGuard guard(e->cfg.device);
   StepArgs a = make_args(e);
   a.obs = (uint8_t*)obs_dev;
+  CUDA_TRY(cudaMemsetAsync(e->d_regen_flag, 0, (size_t)e->cfg.num_envs, (cudaStream_t)stream));
   return launch(e, a, OP_RESET, (cudaStream_t)stream);
 }
 
@@ -673,7 +763,9 @@ int pgm_step(pgm_engine* e, const void* actions_dev, int32_t action_itemsize, vo
   a.rewards = rewards_dev;
   a.terminated = terminated_dev;
   a.truncated = truncated_dev;
-  return launch(e, a, OP_STEP, (cudaStream_t)stream);
+  int rc = launch(e, a, OP_STEP, (cudaStream_t)stream);
+  if (rc != PGM_OK || e->cfg.auto_reset != 2) return rc;
+  return enqueue_rebuilds(e, obs_dev, (cudaStream_t)stream);
 }
 
 int pgm_step_many(pgm_engine* e, int32_t num_steps, const void* actions_dev, int32_t action_itemsize, void* obs_dev,
@@ -686,6 +778,8 @@ int pgm_step_many(pgm_engine* e, int32_t num_steps, const void* actions_dev, int
     return fail(PGM_ERR_INVALID, "action_itemsize must be 1, 2, 4 or 8");
   if (obs_dev && obs_ring < 1) return fail(PGM_ERR_INVALID, "obs_ring must be >= 1");
   if (!e->tasks_ready) return fail(PGM_ERR_STATE, "pgm_step_many before pgm_generate / pgm_set_tasks");
+  if (e->cfg.auto_reset == 2 && num_steps > 1)
+    return fail(PGM_ERR_UNSUPPORTED, "auto_reset=2 rebuilds tasks between launches: use one step per launch");
   DeviceGuard guard(e->cfg.device);
   const long long NA = (long long)e->cfg.num_envs * e->cfg.num_agents;
   StepArgs a = make_args(e);
@@ -889,10 +983,12 @@ int pgm_check_errors(pgm_engine* e, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(&flag, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
-  if (flag & 1) {
-    CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), s));
-    return fail(PGM_ERR_ACTION, "an action outside [0,5) was passed to pgm_step (treated as 0 = stay)");
-  }
+  if (flag) CUDA_TRY(cudaMemsetAsync(e->d_err, 0, sizeof(int), s));
+  if (flag & 1) return fail(PGM_ERR_ACTION, "an action outside [0,5) was passed to pgm_step (treated as 0 = stay)");
+  if (flag & 4)
+    return fail(PGM_ERR_OVERFLOW,
+                "Can't create task for a new seed during auto_reset=2 (upstream would retry or raise OverflowError); "
+                "the instance was reset to its previous task");
   return PGM_OK;
 }
 

@@ -9,8 +9,12 @@ namespace pgm {
 
 struct DevGenArgs {
   int first, count;        // instances [first, first+count) unless `index` is given
-  const int* index;        // optional device array [count] of instance indices
-  const uint64_t* seeds;   // device [count]
+  const int* index;        // optional device array [count] of instance indices (regeneration mode)
+  const int* count_ptr;    // regeneration mode: number of entries of `index` (device scalar)
+  const uint64_t* seeds;   // device [count] (direct mode)
+  const uint64_t* cur_seeds;  // regeneration mode: seed of instance n = cur_seeds[n]
+  int slots;               // scratch slots = warps of the launch; warp w handles entries w, w+slots, ...
+  int* err_flag;           // regeneration mode: sticky engine error flag (bit 2: task could not be rebuilt)
   int H, W, A, r, lifelong;
   const uint8_t* map;      // optional device map [H][W] shared by all instances
   // numpy random_binomial(p, n=1) constants computed on the host (libm exp/log)
@@ -38,5 +42,8 @@ struct DevGenArgs {
 
 long long devgen_scratch_bytes(int HW, int A, int count);
 int launch_devgen(const DevGenArgs& a, cudaStream_t s);  // returns a cudaError_t
+// flags[n] != 0 -> index[count++] = n, cur_seeds[n] += stride
+int launch_regen_compact(int N, const uint8_t* flags, uint64_t* cur_seeds, uint64_t stride, int* index, int* count,
+                         cudaStream_t s);
 
 }  // namespace pgm

@@ -75,6 +75,8 @@ struct StepArgs {
   uint8_t* terminated;
   uint8_t* truncated;
   int* err_flag;
+  uint8_t* regen_flag;  // auto_reset == 2: set to 1 when the episode of instance n ended (task is rebuilt after the step)
+  const uint8_t* mask;  // OP_OBSERVE only: if not NULL, only instances with mask[n] != 0 are observed (and regen_flag[n] cleared)
   long long* debug;     // optional [N][16] clock64 stamps at phase boundaries (tools/phase_timeline.py)
   // shared memory layout, byte offsets inside a team slice
   int off_obst, off_abits, off_occ, off_pos, off_tgt, off_npos, off_link, off_act, off_flag, off_misc;
@@ -393,6 +395,7 @@ __global__ void __launch_bounds__(1024, 1)
   const int tid = threadIdx.x % TEAM;
   const int n = blockIdx.x * p.teams_per_cta + team;
   if (n >= p.N) return;  // whole team leaves together
+  if (OP == OP_OBSERVE && p.mask != nullptr && p.mask[n] == 0) return;
   const int bar_id = 1 + team;
   unsigned char* base = smem_raw + (size_t)team * p.team_smem;
   uint32_t* s_obst = reinterpret_cast<uint32_t*>(base + p.off_obst);
@@ -633,7 +636,8 @@ __global__ void __launch_bounds__(1024, 1)
       const bool solved = (c_was == A);
       const bool all_term = (ONTGT == 2) ? false : (c_on == A);
       const bool done = trunc || all_term;
-      const bool do_reset = done && p.auto_reset;
+      const bool do_reset = done && p.auto_reset == 1;
+      const bool reseed = done && p.auto_reset == 2;  // new task from a new seed: built after this launch
       const long long oa = ia + (long long)k * p.out_step_stride;  // outputs of step k
 
       for (int a = tid; a < A; a += TEAM) {
@@ -697,9 +701,11 @@ __global__ void __launch_bounds__(1024, 1)
           m_acc2 = mstep + 1;
         }
         step_idx = do_reset ? 0 : step_idx + 1;
+      if (reseed) obs_k = nullptr;  // the observation of the rebuilt task is written by the masked observe pass
         if (tid == 0) {
           p.elapsed[n] = step_idx;
           p.episode_done[n] = done ? 1 : 0;
+          if (reseed) p.regen_flag[n] = 1;
           *reinterpret_cast<int4*>(p.metric_acc + 4 * (long long)n) = make_int4(m_acc0, m_acc1, m_acc2, 0);
         }
       }
@@ -728,6 +734,7 @@ __global__ void __launch_bounds__(1024, 1)
       // (emit_observations starts with stage zeroing + team_sync, which also orders the atomics)
       // ---- phase 5/6: observation bits, expansion, stores -------------------------
       emit_observations<TEAM, RT>(p, obs_k, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
+      if (OP == OP_OBSERVE && p.mask != nullptr && tid == 0) p.regen_flag[n] = 0;
     }
     if (k + 1 < num_steps) team_sync<TEAM>(bar_id);  // stage (aliasing occ) and s_act are rewritten next
   }

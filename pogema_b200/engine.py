@@ -17,8 +17,8 @@ def _ptr(a: Optional[np.ndarray]):
 class Engine:
     """N instances of one GridConfig shape on one CUDA device."""
 
-    def __init__(self, grid_config: GridConfig, num_envs: int, device: int = 0, auto_reset: bool = False,
-                 obs_format: str = "u8", team_threads: int = 0):
+    def __init__(self, grid_config: GridConfig, num_envs: int, device: int = 0, auto_reset=False,
+                 obs_format: str = "u8", team_threads: int = 0, reseed_stride: int = 0):
         self.lib = nat.load()
         gc = grid_config
         if gc.observation_type != 'default':
@@ -34,7 +34,8 @@ class Engine:
         cfg.max_episode_steps = int(gc.max_episode_steps)
         cfg.collision_system = nat.COLLISION[gc.collision_system]
         cfg.on_target = nat.ON_TARGET[gc.on_target]
-        cfg.auto_reset = 1 if auto_reset else 0
+        cfg.auto_reset = 2 if auto_reset == "reseed" else (1 if auto_reset else 0)
+        cfg.reserved[0] = int(reseed_stride)
         cfg.obs_format = nat.OBS_FORMAT[obs_format]
         cfg.team_threads = int(team_threads)
         self.cfg = cfg

@@ -40,4 +40,5 @@ def make_sharded_env(grid_config, num_instances: int, rank: int, world_size: int
     from .batched import BatchedPogema
     base = (grid_config.seed or 0) if base_seed is None else base_seed
     seeds = shard_seeds(base, num_instances, rank, world_size)
+    kwargs.setdefault("reseed_stride", int(num_instances))  # new seeds never collide across ranks
     return BatchedPogema(grid_config, num_envs=len(seeds), device=device, seeds=seeds, **kwargs)

@@ -101,3 +101,45 @@ def test_device_generation_is_fast():
     dt = time.perf_counter() - t0
     print(f"device regeneration of 4096 instances: {dt * 1e3:.2f} ms")
     assert dt < 0.25
+
+
+@pytest.mark.parametrize("ot,coll", [("finish", "priority"), ("restart", "soft"), ("nothing", "block_both")])
+def test_auto_reset_with_new_seeds_matches_oracle(ot, coll):
+    """auto_reset='reseed': every finished episode is followed by a task built from seed + stride,
+    i.e. a fresh oracle env with that seed."""
+    import torch
+    from oracle import pogema_oracle as orc
+    from pogema_b200 import BatchedPogema, GridConfig
+    kw = dict(size=8, density=0.25, num_agents=3, obs_radius=3, max_episode_steps=6, collision_system=coll,
+              on_target=ot)
+    seeds = [3, 4, 5, 6, 7]
+    stride = 100
+    env = BatchedPogema(GridConfig(**kw), num_envs=len(seeds), seeds=seeds, auto_reset="reseed", reseed_stride=stride)
+    obs = env.reset().cpu().numpy()
+    cur = list(seeds)
+    refs = []
+    for k, s in enumerate(seeds):
+        r = orc.pogema_v0(orc.GridConfig(seed=s, **kw))
+        o, _ = r.reset()
+        assert np.array_equal(obs[k], np.stack(o).astype(np.uint8))
+        refs.append(r)
+    rng = np.random.default_rng(0)
+    episodes = 0
+    for t in range(40):
+        acts = rng.integers(0, 5, size=(len(seeds), kw["num_agents"])).astype(np.uint8)
+        o, r, te, tr = env.step(torch.from_numpy(acts).cuda())
+        o, r, te, tr = o.cpu().numpy(), r.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy()
+        for k in range(len(seeds)):
+            ro, rr, rte, rtr, _ = refs[k].step(list(acts[k]))
+            assert np.array_equal(r[k], np.array(rr, dtype=np.float32)) and np.array_equal(te[k], np.array(rte))
+            assert np.array_equal(tr[k], np.array(rtr))
+            if all(rte) or all(rtr):
+                cur[k] += stride
+                refs[k] = orc.pogema_v0(orc.GridConfig(seed=cur[k], **kw))
+                ro, _ = refs[k].reset()
+                episodes += 1
+            assert np.array_equal(o[k], np.stack(ro).astype(np.uint8)), (t, k)
+    assert episodes >= 25
+    env.check_errors()
+    with pytest.raises(Exception):
+        env.rollout(torch.zeros((4, len(seeds), kw["num_agents"]), dtype=torch.uint8, device="cuda"))
