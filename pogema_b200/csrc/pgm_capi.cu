@@ -64,7 +64,7 @@ struct pgm_engine {
   bool tasks_ready = false;
   int sm_count = 148;
   // plan
-  int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1;
+  int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1, occ_mode = 0;
   StepArgs layout{};  // offsets only
   // device state
   uint32_t* d_obst = nullptr;
@@ -104,27 +104,46 @@ struct pgm_engine {
 
 namespace {
 
-int compute_plan(pgm_engine* e) {
-  const pgm_config& c = e->cfg;
-  const int A = c.num_agents;
-  const int occ_bytes = round_up(e->PH * e->PW * 2 + 4, 16);
+// Shared-memory layout of one instance for a given occupancy structure and observation batch.
+struct Layout {
+  StepArgs L{};
+  int occ_mode = 0, batch_agents = 0, team_smem = 0;
+};
+
+bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* out) {
+  const int A = e->cfg.num_agents;
+  const int smem_max = 227 * 1024;
+  int tiles = 0, tiles_w = 0, tshift = 0, occ_bytes;
+  if (occ_mode == 0) {
+    occ_bytes = round_up(e->PH * e->PW * 2 + 4, 16);
+  } else {
+    // tile buckets: 4x4 tiles, coarser while the head array is larger than 16 KB
+    tshift = 2;
+    for (;;) {
+      tiles_w = (e->PW + (1 << tshift) - 1) >> tshift;
+      tiles = round_up(((e->PH + (1 << tshift) - 1) >> tshift) * tiles_w, 4);
+      if (tiles * 4 <= 16 * 1024 || tshift >= 6) break;
+      tshift++;
+    }
+    occ_bytes = round_up(tiles * 4 + A * 2, 16);
+  }
   const int fixed = e->obst_stride * 4 + round_up((e->PH * e->WPR + 1) * 4, 16) + 4 * round_up(A * 4, 16) +
                     2 * round_up(A, 16) + 16;
-  const int smem_max = 227 * 1024;
-  // observation batch: as many agents as fit next to the fixed part (at least what occ needs anyway)
-  long long budget = std::max<long long>(occ_bytes, 64 * 1024);
+  if (fixed + occ_bytes > smem_max) return false;
+  // observation stage: aliases the occupancy region, so at least that much is free; beyond it take what
+  // still lets `want_resident` instances share an SM, but never less than 32 agents (or all of them)
+  const long long per_agent_bits = e->stage_bpa;
+  auto stage_bytes_for = [&](long long g) { return (long long)round_up((int)(((g * per_agent_bits + 31) / 32 + 2) * 4), 16); };
+  const long long target = smem_max / std::max(1, want_resident);
+  long long budget = std::max<long long>(occ_bytes, target - fixed);
+  budget = std::max<long long>(budget, stage_bytes_for(std::min(A, 32)));
   budget = std::min<long long>(budget, (long long)smem_max - fixed);
-  if (budget < occ_bytes)
-    return fail(PGM_ERR_UNSUPPORTED,
-                "instance does not fit in shared memory (needs %d + %d bytes of %d): map %dx%d, %d agents",
-                fixed, occ_bytes, smem_max, c.height, c.width, A);
-  long long g = ((budget - 16) * 8) / e->stage_bpa;
-  if (g < 1)
-    return fail(PGM_ERR_UNSUPPORTED, "observation of one agent (%d bits) does not fit the stage buffer",
-                e->stage_bpa);
-  e->batch_agents = (int)std::min<long long>(g, A);
-  const int stage_bytes = round_up((int)((((long long)e->batch_agents * e->stage_bpa + 31) / 32 + 2) * 4), 16);
-  StepArgs& L = e->layout;
+  budget = std::min<long long>(budget, std::max<long long>(stage_bytes_for(A), occ_bytes));
+  long long g = ((budget - 16) * 8) / per_agent_bits;
+  if (g < 1) return false;
+  g = std::min<long long>(g, A);
+  const int stage_bytes = (int)stage_bytes_for(g);
+  StepArgs& L = out->L;
   int off = 0;
   L.off_obst = off;
   off += e->obst_stride * 4;
@@ -147,13 +166,51 @@ int compute_plan(pgm_engine* e) {
   L.off_misc = off;
   off += 16;
   L.team_smem = round_up(off, 16);
-  if (L.team_smem > smem_max)
-    return fail(PGM_ERR_UNSUPPORTED, "instance needs %d bytes of shared memory (max %d)", L.team_smem, smem_max);
+  L.occ_tiles = tiles;
+  L.occ_tiles_w = tiles_w;
+  L.occ_tshift = tshift;
+  if (L.team_smem > smem_max) return false;
+  out->occ_mode = occ_mode;
+  out->batch_agents = (int)g;
+  out->team_smem = L.team_smem;
+  return true;
+}
+
+int compute_plan(pgm_engine* e) {
+  const pgm_config& c = e->cfg;
+  const int A = c.num_agents;
+  const int smem_max = 227 * 1024;
+  const int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;  // instances an SM has to host
+  // dense cell->agent grid when it lets an SM host what the job needs (one LDS per lookup), else tile buckets
+  Layout dense, hash, *use = nullptr;  // `hash` = the tile-bucket layout
+  const bool ok_d = make_layout(e, 0, per_sm, &dense);
+  const bool ok_h = make_layout(e, 1, per_sm, &hash);
+  // threads an SM can keep busy under a layout: resident instances x team size (team <= agents, pow2)
+  auto busy_threads = [&](bool ok, const Layout& l) {
+    if (!ok) return 0;
+    const int resident = std::max(1, std::min(per_sm, smem_max / l.team_smem));
+    int team = pow2_floor(std::max(32, 1024 / resident));
+    team = std::min(team, std::max(32, pow2_ceil(A)));
+    return resident * team;
+  };
+  const int thr_d = busy_threads(ok_d, dense), thr_h = busy_threads(ok_h, hash);
+  int force = -1;
+  if (const char* v = getenv("PGM_OCC")) force = atoi(v);  // tuning knob: 0 dense grid, 1 tile buckets
+  if (force == 0 && ok_d) use = &dense;
+  else if (force == 1 && ok_h) use = &hash;
+  else if (ok_d && thr_d >= thr_h) use = &dense;  // ties go to the dense grid (cheaper lookups)
+  else if (ok_h) use = &hash;
+  if (!use)
+    return fail(PGM_ERR_UNSUPPORTED,
+                "one instance does not fit in 227 KB of shared memory: map %dx%d (padded %dx%d), %d agents, r=%d",
+                c.height, c.width, e->PH, e->PW, A, c.obs_radius);
+  e->layout = use->L;
+  e->occ_mode = use->occ_mode;
+  e->batch_agents = use->batch_agents;
+  StepArgs& L = e->layout;
   int team = c.team_threads;
   if (team == 0) {
-    // ~1024 threads per SM (64 registers each) shared by the instances an SM hosts at a time:
-    // as many as the job needs per SM, unless shared memory allows fewer
-    const int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;
+    // ~1024 threads per SM (64 registers each) shared by the instances an SM hosts at a time
     const int resident = std::max(1, std::min(per_sm, smem_max / L.team_smem));
     team = pow2_floor(std::max(32, 1024 / resident));
     team = std::min(team, std::max(32, pow2_ceil(A)));
@@ -173,7 +230,6 @@ int compute_plan(pgm_engine* e) {
     for (int t = 1; t <= max_tpc; ++t) {
       const int grid = (c.num_envs + t - 1) / t;
       const int per_sm_ctas = (grid + e->sm_count - 1) / e->sm_count;
-      // CTAs resident at once are limited by shared memory and threads; extra CTAs run as later waves
       const double busiest = (double)per_sm_ctas * t;
       double score = ideal / busiest;
       const int threads = t * team;
@@ -197,7 +253,7 @@ int compute_plan(pgm_engine* e) {
 
 int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
   LaunchDims d{e->team, static_radius(e->cfg.obs_radius), e->grid, e->cta_threads, e->smem_cta, e->cfg.device,
-               e->use_pdl ? 1 : 0};
+               e->use_pdl ? 1 : 0, e->occ_mode};
   int err;
   if (op == OP_OBSERVE) err = launch_observe(d, a, s);
   else if (op == OP_RESET) err = launch_reset(d, a, s);
@@ -572,7 +628,7 @@ int64_t pgm_launch_count(const pgm_engine* e) { return e ? e->launches : 0; }
 
 int pgm_plan(const pgm_engine* e, int32_t* out, int32_t n) {
   if (!e || !out) return fail(PGM_ERR_INVALID, "null argument");
-  const int32_t v[7] = {e->team, e->tpc, e->cta_threads, e->smem_cta, e->grid, e->batch_agents, 1};
+  const int32_t v[7] = {e->team, e->tpc, e->cta_threads, e->smem_cta, e->grid, e->batch_agents, e->occ_mode};
   for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
   return PGM_OK;
 }

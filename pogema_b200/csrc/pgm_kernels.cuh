@@ -82,6 +82,7 @@ struct StepArgs {
   int off_obst, off_abits, off_occ, off_pos, off_tgt, off_npos, off_link, off_act, off_flag, off_misc;
   int team_smem;
   int teams_per_cta;
+  int occ_tiles, occ_tiles_w, occ_tshift;  // OCC == 1: number of tiles (padded to 4), tiles per row, log2(tile side)
 };
 
 // ------------------------------------------------------------------------- //
@@ -159,17 +160,53 @@ __device__ __forceinline__ uint32_t bit_at(const uint32_t* bits, int WPR, int x,
   return (bits[x * WPR + (y >> 5)] >> (y & 31)) & 1u;
 }
 
+// Pre-move occupancy lookup "which active agent stands on cell (x,y)":
+//   OCC == 0: dense uint16 grid over the padded map (one LDS per lookup; small maps)
+//   OCC == 1: tile buckets - the padded map is cut into 2^t x 2^t tiles, every tile heads a linked list
+//             of the agents standing in it (ATOMS.EXCH insert, no probing loops).  Memory ~ cells / 4^t
+//             + agents: large maps keep several instances per SM (256x256 with 1024 agents: 4 per SM).
+template <int OCC>
+struct OccMap {
+  uint16_t* dense;       // OCC 0
+  uint32_t* heads;       // OCC 1: [tiles] first agent of the tile or 0xFFFFFFFF
+  uint16_t* next;        // OCC 1: [A] next agent in the same tile or OCC_NONE
+  const uint32_t* pos;   // OCC 1: packed pre-move positions of the agents
+  int tshift, tiles_w;
+  int PW;
+  __device__ __forceinline__ void insert(int x, int y, uint32_t a) const {
+    if (OCC == 0) {
+      dense[x * PW + y] = (uint16_t)a;
+    } else {
+      const uint32_t prev = atomicExch(&heads[(x >> tshift) * tiles_w + (y >> tshift)], a);
+      next[a] = (uint16_t)prev;  // 0xFFFFFFFF -> OCC_NONE
+    }
+  }
+  __device__ __forceinline__ uint32_t lookup(int x, int y) const {
+    if (OCC == 0) {
+      return dense[x * PW + y];
+    } else {
+      const uint32_t key = (uint32_t)x | ((uint32_t)y << 16);
+      uint32_t k = heads[(x >> tshift) * tiles_w + (y >> tshift)] & 0xFFFFu;
+      while (k != OCC_NONE) {
+        if (pos[k] == key) return k;
+        k = next[k];
+      }
+      return OCC_NONE;
+    }
+  }
+};
+
 // Is some agent other than the one standing on (sx,sy) heading into (tx,ty)?
 // kind 0: any claimant;  kind 1: a claimant with lo < index < hi.
-template <int KIND>
-__device__ __forceinline__ bool other_claimant(const uint16_t* occ, const uint8_t* act, int PW, int tx, int ty,
-                                               int sx, int sy, int lo, int hi) {
+template <int KIND, int OCC>
+__device__ __forceinline__ bool other_claimant(const OccMap<OCC>& occ, const uint8_t* act, int tx, int ty, int sx, int sy,
+                                               int lo, int hi) {
   bool found = false;
 #pragma unroll
   for (int m = 1; m <= 4; ++m) {
     int nx = tx + move_dx(m), ny = ty + move_dy(m);
     if (nx == sx && ny == sy) continue;
-    uint32_t k = occ[nx * PW + ny];
+    uint32_t k = occ.lookup(nx, ny);
     if (k != OCC_NONE && act[k] == opposite(m)) {
       if (KIND == 0) found = true;
       else if ((int)k > lo && (int)k < hi) found = true;
@@ -387,7 +424,7 @@ __device__ __forceinline__ uint32_t st_active(uint32_t w) { return (w >> 15) & 1
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-template <int TEAM, int COLL, int OP, int RT>
+template <int TEAM, int COLL, int OP, int RT, int OCC>
 __global__ void __launch_bounds__(1024, 1)
     pgm_step_kernel(const StepArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -400,9 +437,16 @@ __global__ void __launch_bounds__(1024, 1)
   unsigned char* base = smem_raw + (size_t)team * p.team_smem;
   uint32_t* s_obst = reinterpret_cast<uint32_t*>(base + p.off_obst);
   uint32_t* s_abits = reinterpret_cast<uint32_t*>(base + p.off_abits);
-  uint16_t* s_occ = reinterpret_cast<uint16_t*>(base + p.off_occ);
+  OccMap<OCC> occ;
+  occ.dense = reinterpret_cast<uint16_t*>(base + p.off_occ);
+  occ.heads = reinterpret_cast<uint32_t*>(base + p.off_occ);
+  occ.next = reinterpret_cast<uint16_t*>(base + p.off_occ + 4 * p.occ_tiles);
+  occ.tshift = p.occ_tshift;
+  occ.tiles_w = p.occ_tiles_w;
+  occ.PW = p.PW;
   uint32_t* s_stage = reinterpret_cast<uint32_t*>(base + p.off_occ);  // aliases occ
   uint32_t* s_pos = reinterpret_cast<uint32_t*>(base + p.off_pos);
+  occ.pos = s_pos;
   uint32_t* s_tgt = reinterpret_cast<uint32_t*>(base + p.off_tgt);
   uint32_t* s_npos = reinterpret_cast<uint32_t*>(base + p.off_npos);
   uint32_t* s_link = reinterpret_cast<uint32_t*>(base + p.off_link);
@@ -477,8 +521,9 @@ __global__ void __launch_bounds__(1024, 1)
       uint4* a4 = reinterpret_cast<uint4*>(s_abits);
       for (int w = tid; w < abits_vec; w += TEAM) a4[w] = make_uint4(0u, 0u, 0u, 0u);
       if (OP == OP_STEP) {
-        const int occ_vec = (p.PH * PW * 2 + 4 + 15) >> 4;
-        uint4* o4 = reinterpret_cast<uint4*>(s_occ);
+        // dense: every cell = OCC_NONE; buckets: every tile head = empty (both are all-ones fills)
+        const int occ_vec = (OCC == 0) ? ((p.PH * PW * 2 + 4 + 15) >> 4) : ((p.occ_tiles + 3) >> 2);
+        uint4* o4 = reinterpret_cast<uint4*>(occ.dense);
         for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
         if (tid == 0) {
           s_cnt[0] = 0;
@@ -512,7 +557,7 @@ __global__ void __launch_bounds__(1024, 1)
       for (int a = tid; a < A; a += TEAM) {
         if (s_flag[a] & 1u) {
           const uint32_t pp = s_pos[a];
-          s_occ[(pp & 0xFFFF) * PW + (pp >> 16)] = (uint16_t)a;
+          occ.insert(pp & 0xFFFF, pp >> 16, a);
         }
       }
       team_sync<TEAM>(bar_id);
@@ -531,7 +576,7 @@ __global__ void __launch_bounds__(1024, 1)
             if (bit_at(s_obst, WPR, tx, ty)) {
               eff = 0u;
             } else {
-              const uint32_t j = s_occ[tx * PW + ty];
+              const uint32_t j = occ.lookup(tx, ty);
               if (j != OCC_NONE && s_act[j] == opposite(act)) eff = 0u;
             }
           }
@@ -551,10 +596,10 @@ __global__ void __launch_bounds__(1024, 1)
           const int sx = pp & 0xFFFF, sy = pp >> 16;
           const int tx = sx + move_dx(act), ty = sy + move_dy(act);
           if (!bit_at(s_obst, WPR, tx, ty)) {
-            const uint32_t j = s_occ[tx * PW + ty];
+            const uint32_t j = occ.lookup(tx, ty);
             if (COLL == 1) {
               // block_both: free cell, sole claimant
-              if (j == OCC_NONE && !other_claimant<0>(s_occ, s_act, PW, tx, ty, sx, sy, 0, 0)) link = ST_OK;
+              if (j == OCC_NONE && !other_claimant<0, OCC>(occ, s_act, tx, ty, sx, sy, 0, 0)) link = ST_OK;
             } else if (COLL == 0) {
               // priority: occupant must have a lower index and leave; first claimant above it wins
               bool ok = true;
@@ -563,12 +608,12 @@ __global__ void __launch_bounds__(1024, 1)
                 if ((int)j > a || s_act[j] == 0) ok = false;
                 else lo = (int)j;
               }
-              if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, lo, a)) ok = false;
+              if (ok && other_claimant<1, OCC>(occ, s_act, tx, ty, sx, sy, lo, a)) ok = false;
               if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
             } else {
               // soft: no stayer on the cell, lowest-index claimant, occupant must leave
               bool ok = !(j != OCC_NONE && s_act[j] == 0);
-              if (ok && other_claimant<1>(s_occ, s_act, PW, tx, ty, sx, sy, -1, a)) ok = false;
+              if (ok && other_claimant<1, OCC>(occ, s_act, tx, ty, sx, sy, -1, a)) ok = false;
               if (ok) link = (j == OCC_NONE) ? ST_OK : (ST_PEND | (j << 2));
             }
           }

@@ -7,13 +7,13 @@
 namespace pgm {
 
 struct LaunchDims {
-  int team, rt, grid, block, smem, device, pdl;
+  int team, rt, grid, block, smem, device, pdl, occ;
 };
 
 // returns a cudaError_t as int
-template <int TEAM, int COLL, int OP, int RT>
+template <int TEAM, int COLL, int OP, int RT, int OCC>
 int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
-  auto kern = pgm_step_kernel<TEAM, COLL, OP, RT>;
+  auto kern = pgm_step_kernel<TEAM, COLL, OP, RT, OCC>;
   static thread_local int configured_dev = -1;
   static thread_local int configured_smem = -1;
   if (configured_dev != d.device || configured_smem < d.smem) {
@@ -37,14 +37,23 @@ int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   return (int)cudaLaunchKernelEx(&cfg, kern, a);
 }
 
+template <int TEAM, int COLL, int OP, int OCC>
+int launch_rt_occ(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
+  switch (d.rt) {
+    case 3: return launch_exact<TEAM, COLL, OP, 3, OCC>(d, a, s);
+    case 5: return launch_exact<TEAM, COLL, OP, 5, OCC>(d, a, s);
+    case 7: return launch_exact<TEAM, COLL, OP, 7, OCC>(d, a, s);
+    default: return launch_exact<TEAM, COLL, OP, 0, OCC>(d, a, s);
+  }
+}
+
 template <int TEAM, int COLL, int OP>
 int launch_rt(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
-  switch (d.rt) {
-    case 3: return launch_exact<TEAM, COLL, OP, 3>(d, a, s);
-    case 5: return launch_exact<TEAM, COLL, OP, 5>(d, a, s);
-    case 7: return launch_exact<TEAM, COLL, OP, 7>(d, a, s);
-    default: return launch_exact<TEAM, COLL, OP, 0>(d, a, s);
+  // the occupancy structure only exists in the step path
+  if constexpr (OP == OP_STEP) {
+    if (d.occ == 1) return launch_rt_occ<TEAM, COLL, OP, 1>(d, a, s);
   }
+  return launch_rt_occ<TEAM, COLL, OP, 0>(d, a, s);
 }
 
 template <int COLL, int OP>

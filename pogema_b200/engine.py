@@ -189,5 +189,5 @@ class Engine:
         out = (C.c_int32 * 7)()
         nat.check(self.lib.pgm_plan(self.handle, out, 7))
         keys = ["team_threads", "teams_per_cta", "cta_threads", "smem_bytes_per_cta", "grid",
-                "agents_per_obs_batch", "workspace_in_smem"]
+                "agents_per_obs_batch", "occupancy_buckets"]
         return dict(zip(keys, [int(v) for v in out]))

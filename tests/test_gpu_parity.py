@@ -144,3 +144,29 @@ def test_multi_step_launch_equals_single_steps(coll, ot):
     c.rollout(act, obs_out=ring)
     for k in range(K - 4, K):
         assert torch.equal(ring[k % 4], obs[k])
+
+
+@pytest.mark.parametrize("coll,ot", list(itertools.product(COLLISIONS, ON_TARGETS)))
+def test_bucket_occupancy_variant(coll, ot, monkeypatch):
+    """The tile-bucket occupancy structure (chosen automatically for large maps) forced on crowded small maps."""
+    monkeypatch.setenv("PGM_OCC", "1")
+    gc = dict(size=10, density=0.1, num_agents=40, obs_radius=3, max_episode_steps=32, collision_system=coll,
+              on_target=ot)
+    gpu = compare(gc, seeds=list(range(200, 216)), T=40, auto_reset=True)
+    assert gpu["env"].engine.plan()["occupancy_buckets"] == 1
+
+
+@pytest.mark.parametrize("coll", COLLISIONS)
+def test_large_map_few_agents(coll):
+    """A 400x400 map does not fit a dense cell grid in shared memory: the planner must pick the tile buckets."""
+    gc = dict(size=400, density=0.2, num_agents=24, obs_radius=4, max_episode_steps=16, collision_system=coll,
+              on_target="finish")
+    gpu = compare(gc, seeds=[1, 2], T=12)
+    assert gpu["env"].engine.plan()["occupancy_buckets"] == 1
+
+
+def test_unsupported_size_fails_loudly():
+    from pogema_b200 import BatchedPogema, GridConfig
+    from pogema_b200._native import PgmError
+    with pytest.raises(PgmError, match="does not fit"):
+        BatchedPogema(GridConfig(size=1024, density=0.1, num_agents=4, seed=0), num_envs=1, generate_on_device=False)
