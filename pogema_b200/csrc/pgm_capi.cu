@@ -127,7 +127,8 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
     }
     occ_bytes = round_up(tiles * 4 + A * 2, 16);
   }
-  const int fixed = e->obst_stride * 4 + round_up((e->PH * e->WPR + 1) * 4, 16) + 4 * round_up(A * 4, 16) +
+  const int bitmap_bytes = round_up((e->PH * e->WPR + 1) * 4, 16);
+  const int fixed = e->obst_stride * 4 + bitmap_bytes * (occ_mode == 1 ? 2 : 1) + 4 * round_up(A * 4, 16) +
                     2 * round_up(A, 16) + 16;
   if (fixed + occ_bytes > smem_max) return false;
   // observation stage: aliases the occupancy region, so at least that much is free; beyond it take what
@@ -139,7 +140,7 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   budget = std::max<long long>(budget, stage_bytes_for(std::min(A, 32)));
   budget = std::min<long long>(budget, (long long)smem_max - fixed);
   budget = std::min<long long>(budget, std::max<long long>(stage_bytes_for(A), occ_bytes));
-  long long g = ((budget - 16) * 8) / per_agent_bits;
+  long long g = (budget >= stage_bytes_for(A)) ? A : ((budget - 16) * 8) / per_agent_bits;
   if (g < 1) return false;
   g = std::min<long long>(g, A);
   const int stage_bytes = (int)stage_bytes_for(g);
@@ -148,7 +149,9 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   L.off_obst = off;
   off += e->obst_stride * 4;
   L.off_abits = off;
-  off += round_up((e->PH * e->WPR + 1) * 4, 16);
+  off += bitmap_bytes;
+  L.off_pbits = off;
+  if (occ_mode == 1) off += bitmap_bytes;
   L.off_occ = off;
   off += std::max(occ_bytes, stage_bytes);
   L.off_pos = off;
@@ -180,25 +183,23 @@ int compute_plan(pgm_engine* e) {
   const pgm_config& c = e->cfg;
   const int A = c.num_agents;
   const int smem_max = 227 * 1024;
-  const int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;  // instances an SM has to host
-  // dense cell->agent grid when it lets an SM host what the job needs (one LDS per lookup), else tile buckets
+  int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;  // instances an SM has to host
+  if (const char* v = getenv("PGM_RESIDENT")) per_sm = std::max(1, atoi(v));  // tuning knob
+  // Instances an SM should host at a time: what the job needs, but not so many that a team drops
+  // below ~half a thread per agent (measured on 1024-agent instances: 2 x 512 threads beat 4 x 256
+  // and 1 x 1024).  The dense cell->agent grid is used when it reaches that residency (one LDS per
+  // lookup), otherwise the tile buckets (memory ~ agents instead of cells).
+  const int want = std::max(1, std::min(per_sm, std::max(2, 2048 / pow2_ceil(A))));
   Layout dense, hash, *use = nullptr;  // `hash` = the tile-bucket layout
-  const bool ok_d = make_layout(e, 0, per_sm, &dense);
-  const bool ok_h = make_layout(e, 1, per_sm, &hash);
-  // threads an SM can keep busy under a layout: resident instances x team size (team <= agents, pow2)
-  auto busy_threads = [&](bool ok, const Layout& l) {
-    if (!ok) return 0;
-    const int resident = std::max(1, std::min(per_sm, smem_max / l.team_smem));
-    int team = pow2_floor(std::max(32, 1024 / resident));
-    team = std::min(team, std::max(32, pow2_ceil(A)));
-    return resident * team;
-  };
-  const int thr_d = busy_threads(ok_d, dense), thr_h = busy_threads(ok_h, hash);
+  const bool ok_d = make_layout(e, 0, want, &dense);
+  const bool ok_h = make_layout(e, 1, want, &hash);
+  const int res_d = ok_d ? std::min(want, smem_max / dense.team_smem) : 0;
+  const int res_h = ok_h ? std::min(want, smem_max / hash.team_smem) : 0;
   int force = -1;
   if (const char* v = getenv("PGM_OCC")) force = atoi(v);  // tuning knob: 0 dense grid, 1 tile buckets
   if (force == 0 && ok_d) use = &dense;
   else if (force == 1 && ok_h) use = &hash;
-  else if (ok_d && thr_d >= thr_h) use = &dense;  // ties go to the dense grid (cheaper lookups)
+  else if (ok_d && res_d >= res_h) use = &dense;
   else if (ok_h) use = &hash;
   if (!use)
     return fail(PGM_ERR_UNSUPPORTED,
@@ -211,7 +212,7 @@ int compute_plan(pgm_engine* e) {
   int team = c.team_threads;
   if (team == 0) {
     // ~1024 threads per SM (64 registers each) shared by the instances an SM hosts at a time
-    const int resident = std::max(1, std::min(per_sm, smem_max / L.team_smem));
+    const int resident = std::max(1, std::min(want, smem_max / L.team_smem));
     team = pow2_floor(std::max(32, 1024 / resident));
     team = std::min(team, std::max(32, pow2_ceil(A)));
     team = std::min(team, 1024);

@@ -79,6 +79,7 @@ struct StepArgs {
   const uint8_t* mask;  // OP_OBSERVE only: if not NULL, only instances with mask[n] != 0 are observed (and regen_flag[n] cleared)
   long long* debug;     // optional [N][16] clock64 stamps at phase boundaries (tools/phase_timeline.py)
   // shared memory layout, byte offsets inside a team slice
+  int off_pbits;  // OCC == 1: pre-move occupancy bitmap
   int off_obst, off_abits, off_occ, off_pos, off_tgt, off_npos, off_link, off_act, off_flag, off_misc;
   int team_smem;
   int teams_per_cta;
@@ -171,20 +172,23 @@ struct OccMap {
   uint32_t* heads;       // OCC 1: [tiles] first agent of the tile or 0xFFFFFFFF
   uint16_t* next;        // OCC 1: [A] next agent in the same tile or OCC_NONE
   const uint32_t* pos;   // OCC 1: packed pre-move positions of the agents
+  uint32_t* pbits;       // OCC 1: pre-move occupancy bitmap (a miss - the common case - costs one LDS)
   int tshift, tiles_w;
-  int PW;
+  int PW, WPR;
   __device__ __forceinline__ void insert(int x, int y, uint32_t a) const {
     if (OCC == 0) {
       dense[x * PW + y] = (uint16_t)a;
     } else {
       const uint32_t prev = atomicExch(&heads[(x >> tshift) * tiles_w + (y >> tshift)], a);
       next[a] = (uint16_t)prev;  // 0xFFFFFFFF -> OCC_NONE
+      atomicOr(&pbits[x * WPR + (y >> 5)], 1u << (y & 31));
     }
   }
   __device__ __forceinline__ uint32_t lookup(int x, int y) const {
     if (OCC == 0) {
       return dense[x * PW + y];
     } else {
+      if (((pbits[x * WPR + (y >> 5)] >> (y & 31)) & 1u) == 0u) return OCC_NONE;
       const uint32_t key = (uint32_t)x | ((uint32_t)y << 16);
       uint32_t k = heads[(x >> tshift) * tiles_w + (y >> tshift)] & 0xFFFFu;
       while (k != OCC_NONE) {
@@ -441,9 +445,11 @@ __global__ void __launch_bounds__(1024, 1)
   occ.dense = reinterpret_cast<uint16_t*>(base + p.off_occ);
   occ.heads = reinterpret_cast<uint32_t*>(base + p.off_occ);
   occ.next = reinterpret_cast<uint16_t*>(base + p.off_occ + 4 * p.occ_tiles);
+  occ.pbits = reinterpret_cast<uint32_t*>(base + p.off_pbits);
   occ.tshift = p.occ_tshift;
   occ.tiles_w = p.occ_tiles_w;
   occ.PW = p.PW;
+  occ.WPR = p.WPR;
   uint32_t* s_stage = reinterpret_cast<uint32_t*>(base + p.off_occ);  // aliases occ
   uint32_t* s_pos = reinterpret_cast<uint32_t*>(base + p.off_pos);
   occ.pos = s_pos;
@@ -525,6 +531,10 @@ __global__ void __launch_bounds__(1024, 1)
         const int occ_vec = (OCC == 0) ? ((p.PH * PW * 2 + 4 + 15) >> 4) : ((p.occ_tiles + 3) >> 2);
         uint4* o4 = reinterpret_cast<uint4*>(occ.dense);
         for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (OCC == 1) {
+          uint4* p4 = reinterpret_cast<uint4*>(occ.pbits);
+          for (int w = tid; w < abits_vec; w += TEAM) p4[w] = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (tid == 0) {
           s_cnt[0] = 0;
           s_cnt[1] = 0;

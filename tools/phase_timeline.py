@@ -9,9 +9,13 @@ ap.add_argument("--n", type=int, default=4096); ap.add_argument("--agents", type
 ap.add_argument("--size", type=int, default=32); ap.add_argument("--r", type=int, default=5)
 ap.add_argument("--coll", default="priority"); ap.add_argument("--ot", default="finish")
 ap.add_argument("--fmt", default="u8")
+ap.add_argument("--map", default="random")
+ap.add_argument("--team", type=int, default=0)
 a = ap.parse_args()
-gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, collision_system=a.coll, on_target=a.ot)
-env = BatchedPogema(gc, num_envs=a.n, auto_reset=True, obs_format=a.fmt)
+from pogema_b200.maps import maze_map, warehouse_map
+mp = None if a.map == 'random' else (maze_map(a.size, 3) if a.map == 'maze' else warehouse_map(a.size)).tolist()
+gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, collision_system=a.coll, on_target=a.ot, map=mp)
+env = BatchedPogema(gc, num_envs=a.n, auto_reset=True, obs_format=a.fmt, team_threads=a.team)
 env.reset()
 acts = [env.sample_actions() for _ in range(8)]
 bufs = [env.new_obs_buffer() for _ in range(4)]
