@@ -327,14 +327,14 @@ __device__ __forceinline__ void agent_bits_static(const uint32_t* s_obst, const 
 // ------------------------------------------------------------------------- //
 // observation generation: batches of agents -> stage bit stream -> HBM
 // ------------------------------------------------------------------------- //
-#define PGM_STAMP(k)                                                        \
-  do {                                                                      \
-    if (p.debug != nullptr && tid == 0) p.debug[(long long)n * 16 + (k)] = clock64(); \
+#define PGM_STAMP(k)                        \
+  do {                                      \
+    if (dbg != nullptr) dbg[(k)] = clock64(); \
   } while (0)
 
 template <int TEAM, int RT>
-__device__ __forceinline__ void emit_observations(const StepArgs& p, uint8_t* obs, int n, int tid, int bar_id,
-                                                  const uint32_t* s_obst,
+__device__ __forceinline__ void emit_observations(const StepArgs& p, long long* dbg, uint8_t* obs, int n, int tid,
+                                                  int bar_id, const uint32_t* s_obst,
                                                   const uint32_t* s_abits, uint32_t* stage, const uint32_t* s_npos,
                                                   const uint32_t* s_tgt) {
   const int r = (RT > 0) ? RT : p.r;
@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(1024, 1)
   const int A = p.A, PW = p.PW, WPR = p.WPR;
   const int ONTGT = p.on_target;
   const long long ia = (long long)n * A;
+  long long* dbg = (p.debug != nullptr && tid == 0) ? p.debug + (long long)n * 16 : nullptr;  // phase stamps
 
   // Let the next launch in the stream be scheduled as soon as SM resources free up: its
   // prologue (phase 0a) overlaps this grid's tail; its griddepcontrol.wait still waits for
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(1024, 1)
       }
       // (emit_observations starts with stage zeroing + team_sync, which also orders the atomics)
       // ---- phase 5/6: observation bits, expansion, stores -------------------------
-      emit_observations<TEAM, RT>(p, obs_k, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
+      emit_observations<TEAM, RT>(p, dbg, obs_k, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
       if (OP == OP_OBSERVE && p.mask != nullptr && tid == 0) p.regen_flag[n] = 0;
     }
     if (k + 1 < num_steps) team_sync<TEAM>(bar_id);  // stage (aliasing occ) and s_act are rewritten next

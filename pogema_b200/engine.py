@@ -21,8 +21,6 @@ class Engine:
                  obs_format: str = "u8", team_threads: int = 0, reseed_stride: int = 0):
         self.lib = nat.load()
         gc = grid_config
-        if gc.observation_type != 'default':
-            raise NotImplementedError("only observation_type='default' is produced by the kernels")
         h, w = gc.map_shape()
         cfg = nat.PgmConfig()
         cfg.abi_version = nat.PGM_ABI_VERSION

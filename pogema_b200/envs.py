@@ -168,8 +168,6 @@ class Pogema(_Base):
             grid_config = GridConfig(**kwargs)
         elif isinstance(grid_config, dict):
             grid_config = GridConfig(**grid_config)
-        if grid_config.observation_type != 'default':
-            raise NotImplementedError("observation_type must be 'default' (POMAPF/MAPF dict observations are not built)")
         self.grid_config = grid_config
         self._device = int(device)
         self._engine = None
@@ -200,7 +198,29 @@ class Pogema(_Base):
         self._engine.grid_config = gc
 
     def _obs_list(self, obs_u8):
-        return [obs_u8[0, i].astype(np.float32) for i in range(self.grid_config.num_agents)]
+        """upstream envs.py :: Pogema._obs: (3, D, D) float32 arrays, or the POMAPF / MAPF dicts built from the
+        same device-made crops plus the state read back from the engine."""
+        n = self.grid_config.num_agents
+        kind = self.grid_config.observation_type
+        if kind == 'default':
+            return [obs_u8[0, i].astype(np.float32) for i in range(n)]
+        pos = self._engine.get_state(nat.STATE_POSITIONS)[0]
+        tgt = self._engine.get_state(nat.STATE_TARGETS)[0]
+        start = self._initial_xy
+        results = []
+        for i in range(n):
+            results.append({'obstacles': obs_u8[0, i, 0].astype(np.float32),
+                            'agents': obs_u8[0, i, 1].astype(np.float32),
+                            'xy': (int(pos[i][0]) - start[i][0], int(pos[i][1]) - start[i][1]),
+                            'target_xy': (int(tgt[i][0]) - start[i][0], int(tgt[i][1]) - start[i][1])})
+        if kind == 'MAPF':
+            r = self.grid_config.obs_radius
+            global_obstacles = self.grid.get_obstacles()
+            for i in range(n):
+                results[i].update(global_obstacles=global_obstacles)
+                results[i]['global_xy'] = (int(pos[i][0]) + r, int(pos[i][1]) + r)
+                results[i]['global_target_xy'] = (int(tgt[i][0]) + r, int(tgt[i][1]) + r)
+        return results
 
     def _get_infos(self):
         active = self._engine.get_state(nat.STATE_ACTIVE)[0]
@@ -219,6 +239,7 @@ class Pogema(_Base):
         self._multi_action_sampler.update_seed(self.grid_config.seed)
         self._initial_xy = self._engine.get_state(nat.STATE_POSITIONS)[0].tolist()
         self.grid = GridView(self)
+
         pos = self._engine.get_state(nat.STATE_POSITIONS)[0]
         tgt = self._engine.get_state(nat.STATE_TARGETS)[0]
         self.was_on_goal = [bool((pos[i] == tgt[i]).all()) for i in range(self.grid_config.num_agents)]

@@ -200,3 +200,29 @@ def test_explicit_agents_on_generated_map():
         o, r, te, tr, _ = env.step(a)
         ro, rr, rte, rtr, _ = ref.step(a)
         assert all(np.array_equal(x, y) for x, y in zip(o, ro)) and r == rr and te == rte
+
+
+@pytest.mark.parametrize("kind", ["POMAPF", "MAPF"])
+def test_dict_observation_types(kind):
+    """upstream envs.py :: _pomapf_obs / _mapf_obs: dict observations with relative / global coordinates."""
+    from pogema_b200 import GridConfig, pogema_v0
+    kw = dict(size=8, density=0.3, num_agents=3, obs_radius=2, max_episode_steps=12, seed=5, observation_type=kind,
+              on_target="restart")
+    env = pogema_v0(GridConfig(**kw))
+    ref = orc.pogema_v0(orc.GridConfig(**kw))
+
+    def same(a, b):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert set(x) == set(y)
+            for key in x:
+                assert np.array_equal(np.asarray(x[key]), np.asarray(y[key])), key
+
+    o, _ = env.reset()
+    ro, _ = ref.reset()
+    same(o, ro)
+    for t in range(12):
+        a = ref.sample_actions()
+        o = env.step(a)[0]
+        ro = ref.step(a)[0]
+        same(o, ro)
