@@ -64,7 +64,7 @@ struct pgm_engine {
   bool tasks_ready = false;
   int sm_count = 148;
   // plan
-  int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1, occ_mode = 0;
+  int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1, occ_mode = 0, obst_global = 0;
   StepArgs layout{};  // offsets only
   // device state
   uint32_t* d_obst = nullptr;
@@ -107,10 +107,10 @@ namespace {
 // Shared-memory layout of one instance for a given occupancy structure and observation batch.
 struct Layout {
   StepArgs L{};
-  int occ_mode = 0, batch_agents = 0, team_smem = 0;
+  int occ_mode = 0, batch_agents = 0, team_smem = 0, obst_global = 0;
 };
 
-bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* out) {
+bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* out, bool obst_global = false) {
   const int A = e->cfg.num_agents;
   const int smem_max = 227 * 1024;
   int tiles = 0, tiles_w = 0, tshift = 0, occ_bytes;
@@ -128,8 +128,9 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
     occ_bytes = round_up(tiles * 4 + A * 2, 16);
   }
   const int bitmap_bytes = round_up((e->PH * e->WPR + 1) * 4, 16);
-  const int fixed = e->obst_stride * 4 + bitmap_bytes * (occ_mode == 1 ? 2 : 1) + 4 * round_up(A * 4, 16) +
-                    2 * round_up(A, 16) + 16;
+  // obst_global: no staged obstacle bitmap, and the pre-move bitmap aliases the post-move one
+  const int fixed = (obst_global ? 0 : e->obst_stride * 4) + bitmap_bytes * ((occ_mode == 1 && !obst_global) ? 2 : 1) +
+                    4 * round_up(A * 4, 16) + 2 * round_up(A, 16) + 16;
   if (fixed + occ_bytes > smem_max) return false;
   // observation stage: aliases the occupancy region, so at least that much is free; beyond it take what
   // still lets `want_resident` instances share an SM, but never less than 32 agents (or all of them)
@@ -147,11 +148,11 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   StepArgs& L = out->L;
   int off = 0;
   L.off_obst = off;
-  off += e->obst_stride * 4;
+  if (!obst_global) off += e->obst_stride * 4;
   L.off_abits = off;
   off += bitmap_bytes;
-  L.off_pbits = off;
-  if (occ_mode == 1) off += bitmap_bytes;
+  L.off_pbits = obst_global ? L.off_abits : off;
+  if (occ_mode == 1 && !obst_global) off += bitmap_bytes;
   L.off_occ = off;
   off += std::max(occ_bytes, stage_bytes);
   L.off_pos = off;
@@ -174,6 +175,7 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   L.occ_tshift = tshift;
   if (L.team_smem > smem_max) return false;
   out->occ_mode = occ_mode;
+  out->obst_global = obst_global ? 1 : 0;
   out->batch_agents = (int)g;
   out->team_smem = L.team_smem;
   return true;
@@ -201,15 +203,18 @@ int compute_plan(pgm_engine* e) {
   else if (force == 1 && ok_h) use = &hash;
   else if (ok_d && res_d >= res_h) use = &dense;
   else if (ok_h) use = &hash;
+  Layout huge;
+  if (!use && make_layout(e, 1, 1, &huge, true)) use = &huge;  // bitmaps too large: obstacles stay in global memory
   if (!use)
     return fail(PGM_ERR_UNSUPPORTED,
                 "one instance does not fit in 227 KB of shared memory: map %dx%d (padded %dx%d), %d agents, r=%d",
                 c.height, c.width, e->PH, e->PW, A, c.obs_radius);
   e->layout = use->L;
   e->occ_mode = use->occ_mode;
+  e->obst_global = use->obst_global;
   e->batch_agents = use->batch_agents;
   StepArgs& L = e->layout;
-  int team = c.team_threads;
+  int team = use->obst_global ? 1024 : c.team_threads;
   if (team == 0) {
     // ~1024 threads per SM (64 registers each) shared by the instances an SM hosts at a time
     const int resident = std::max(1, std::min(want, smem_max / L.team_smem));
@@ -254,7 +259,7 @@ int compute_plan(pgm_engine* e) {
 
 int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
   LaunchDims d{e->team, static_radius(e->cfg.obs_radius), e->grid, e->cta_threads, e->smem_cta, e->cfg.device,
-               e->use_pdl ? 1 : 0, e->occ_mode};
+               e->use_pdl ? 1 : 0, e->occ_mode, e->obst_global};
   int err;
   if (op == OP_OBSERVE) err = launch_observe(d, a, s);
   else if (op == OP_RESET) err = launch_reset(d, a, s);

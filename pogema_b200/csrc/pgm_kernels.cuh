@@ -428,7 +428,10 @@ __device__ __forceinline__ uint32_t st_active(uint32_t w) { return (w >> 15) & 1
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-template <int TEAM, int COLL, int OP, int RT, int OCC>
+// OG == 1 (maps whose two bitmaps do not fit in shared memory, e.g. 1024x1024): the obstacle bitmap is
+// read from global memory / L2 instead of being staged, and the pre-move bitmap shares storage with the
+// post-move one.
+template <int TEAM, int COLL, int OP, int RT, int OCC, int OG>
 __global__ void __launch_bounds__(1024, 1)
     pgm_step_kernel(const StepArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -439,7 +442,8 @@ __global__ void __launch_bounds__(1024, 1)
   if (OP == OP_OBSERVE && p.mask != nullptr && p.mask[n] == 0) return;
   const int bar_id = 1 + team;
   unsigned char* base = smem_raw + (size_t)team * p.team_smem;
-  uint32_t* s_obst = reinterpret_cast<uint32_t*>(base + p.off_obst);
+  const uint32_t* s_obst = OG ? (p.obst + (long long)n * p.obst_stride)
+                              : reinterpret_cast<const uint32_t*>(base + p.off_obst);
   uint32_t* s_abits = reinterpret_cast<uint32_t*>(base + p.off_abits);
   OccMap<OCC> occ;
   occ.dense = reinterpret_cast<uint16_t*>(base + p.off_occ);
@@ -472,12 +476,12 @@ __global__ void __launch_bounds__(1024, 1)
   pdl_trigger();
   PGM_STAMP(0);
   // ---- phase 0a (independent of the previous launch): obstacle map by bulk copy
-  if (tid == 0) {
+  if (!OG && tid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
     const uint32_t bytes = (uint32_t)p.obst_stride * 4u;
     mbar_expect_tx(s_bar, bytes);
-    bulk_g2s(s_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
+    bulk_g2s(base + p.off_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
   }
   // ---- phase 0b: mutable state of this instance (two agents per thread in flight)
   PGM_STAMP(1);
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(1024, 1)
     }
   }
   team_sync<TEAM>(bar_id);  // the mbarrier was initialised by thread 0 of the team
-  mbar_wait(s_bar, 0);
+  if (!OG) mbar_wait(s_bar, 0);
 
   // One launch advances this instance by p.num_steps steps (1 for pgm_step; >1 for pgm_step_many,
   // where every team runs its own timeline: no grid-wide barrier between steps, the observation
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(1024, 1)
         const int occ_vec = (OCC == 0) ? ((p.PH * PW * 2 + 4 + 15) >> 4) : ((p.occ_tiles + 3) >> 2);
         uint4* o4 = reinterpret_cast<uint4*>(occ.dense);
         for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (OCC == 1) {
+        if (OCC == 1 && p.off_pbits != p.off_abits) {
           uint4* p4 = reinterpret_cast<uint4*>(occ.pbits);
           for (int w = tid; w < abits_vec; w += TEAM) p4[w] = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -657,6 +661,13 @@ __global__ void __launch_bounds__(1024, 1)
         }
       }
       team_sync<TEAM>(bar_id);
+      if (OCC == 1 && p.off_pbits == p.off_abits) {
+        // the pre-move bitmap shared the storage of the post-move one: clear it again
+        const int abits_vec = (p.PH * WPR + 1 + 3) >> 2;
+        uint4* a4 = reinterpret_cast<uint4*>(s_abits);
+        for (int w = tid; w < abits_vec; w += TEAM) a4[w] = make_uint4(0u, 0u, 0u, 0u);
+        team_sync<TEAM>(bar_id);
+      }
       PGM_STAMP(4);
 
       // ---- phase 3: apply moves, on_target bookkeeping, time limit -----------

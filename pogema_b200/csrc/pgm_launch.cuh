@@ -7,13 +7,13 @@
 namespace pgm {
 
 struct LaunchDims {
-  int team, rt, grid, block, smem, device, pdl, occ;
+  int team, rt, grid, block, smem, device, pdl, occ, og;
 };
 
 // returns a cudaError_t as int
-template <int TEAM, int COLL, int OP, int RT, int OCC>
+template <int TEAM, int COLL, int OP, int RT, int OCC, int OG = 0>
 int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
-  auto kern = pgm_step_kernel<TEAM, COLL, OP, RT, OCC>;
+  auto kern = pgm_step_kernel<TEAM, COLL, OP, RT, OCC, OG>;
   static thread_local int configured_dev = -1;
   static thread_local int configured_smem = -1;
   if (configured_dev != d.device || configured_smem < d.smem) {
@@ -56,8 +56,21 @@ int launch_rt(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   return launch_rt_occ<TEAM, COLL, OP, 0>(d, a, s);
 }
 
+// obstacle bitmap in global memory (huge maps): 1024-thread teams, tile buckets only
+template <int COLL, int OP>
+int launch_og(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
+  constexpr int OCC = (OP == OP_STEP) ? 1 : 0;
+  switch (d.rt) {
+    case 3: return launch_exact<1024, COLL, OP, 3, OCC, 1>(d, a, s);
+    case 5: return launch_exact<1024, COLL, OP, 5, OCC, 1>(d, a, s);
+    case 7: return launch_exact<1024, COLL, OP, 7, OCC, 1>(d, a, s);
+    default: return launch_exact<1024, COLL, OP, 0, OCC, 1>(d, a, s);
+  }
+}
+
 template <int COLL, int OP>
 int launch_variant(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
+  if (d.og) return launch_og<COLL, OP>(d, a, s);
   switch (d.team) {
     case 32: return launch_rt<32, COLL, OP>(d, a, s);
     case 64: return launch_rt<64, COLL, OP>(d, a, s);

@@ -165,8 +165,33 @@ def test_large_map_few_agents(coll):
     assert gpu["env"].engine.plan()["occupancy_buckets"] == 1
 
 
-def test_unsupported_size_fails_loudly():
+@pytest.mark.parametrize("coll", COLLISIONS)
+def test_maximum_map_size(coll):
+    """GridConfig's maximum size (1024): the bitmaps no longer fit in shared memory next to each other, the
+    obstacle bitmap is read from global memory.  Compared against the C oracle built from the engine's state."""
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    from tests.test_gpu_fullsize import c_oracle_from_engine
+    gc = dict(size=1024, density=0.3, num_agents=300, obs_radius=5, max_episode_steps=6, collision_system=coll,
+              on_target="finish")
+    env = BatchedPogema(GridConfig(**gc), num_envs=2, seeds=[5, 6], auto_reset=True)
+    obs = env.reset()
+    co = c_oracle_from_engine(env)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = []
+    for t in range(8):
+        a = env.sample_actions(g)
+        acts.append(a.cpu().numpy())
+        obs, rew, term, trunc = env.step(a)
+    out = co.run(np.stack(acts), auto_reset=True)
+    assert np.array_equal(env.get_agents_xy().cpu().numpy() + 5, co.pos)
+    assert np.array_equal(obs.cpu().numpy(), out["obs"])
+    assert np.array_equal(rew.cpu().numpy(), out["rewards"])
+
+
+def test_unsupported_shape_fails_loudly():
+    """More agents than one SM's shared memory can hold scratch for: a clear error, never a silent fallback."""
     from pogema_b200 import BatchedPogema, GridConfig
     from pogema_b200._native import PgmError
     with pytest.raises(PgmError, match="does not fit"):
-        BatchedPogema(GridConfig(size=1024, density=0.1, num_agents=4, seed=0), num_envs=1, generate_on_device=False)
+        BatchedPogema(GridConfig(size=400, density=0.1, num_agents=20000, seed=0), num_envs=1, generate_on_device=False)
