@@ -89,6 +89,35 @@ def oracle_throughput(cores, n_inst_per_core, n_steps, budget_s=0.0, seed0=10_00
     return total / slowest, total, slowest, wall
 
 
+def _c_oracle_worker(args):
+    seed0, n_inst, budget_s = args
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from oracle.c_driver import COracle
+    co = COracle.from_python_oracle(WORKLOAD, list(range(seed0, seed0 + n_inst)))
+    rng = np.random.default_rng(seed0)
+    A = WORKLOAD["num_agents"]
+    T = 64
+    done = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        acts = rng.integers(0, 5, size=(T, n_inst, A)).astype(np.uint8)
+        done += co.run(acts, auto_reset=True, want_obs=True)["agent_steps"]
+    return done, time.perf_counter() - t0
+
+
+def c_oracle_throughput(cores, budget_s=4.0, n_inst=32):
+    """Aggregate agent-steps/s of the C restatement (oracle/step_oracle.c), one process per core."""
+    import multiprocessing as mp
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle_step.so")):
+        return None
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_c_oracle_worker, [(20_000 + c * 1000, n_inst, budget_s) for c in range(cores)])
+    total = sum(r[0] for r in res)
+    return total / max(r[1] for r in res), total
+
+
 # --------------------------------------------------------------------------- #
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
@@ -380,6 +409,14 @@ def run_cuda(args):
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": (f"{cores} processes x 2 instances of the workload shape for ~{args.cpu_seconds:.0f} s "
                            f"({total} agent-steps), Python/numpy restatement of upstream pogema (oracle/pogema_oracle.py)")}
+            try:
+                c_res = c_oracle_throughput(cores)
+            except Exception:
+                c_res = None
+            if c_res:
+                # context only: a plain-C restatement of the same path (not how the reference is implemented)
+                line["cpu_baseline_c"] = {"value": c_res[0], "unit": UNIT, "cores": cores, "kind": "port (C, oracle/step_oracle.c)",
+                                          "sample": f"{cores} processes x 32 instances for ~4 s ({c_res[1]} agent-steps)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

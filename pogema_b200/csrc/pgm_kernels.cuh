@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(1024, 1)
   // where every team runs its own timeline: no grid-wide barrier between steps, the observation
   // stores of one instance overlap the move phases of the others).
   const int num_steps = (OP == OP_STEP) ? p.num_steps : 1;
+  int obs_slot = 0;  // k % obs_ring without a division per step
 #pragma unroll 1
   for (int k = 0; k < num_steps; ++k) {
     // ---- per-step fills (both regions are padded to multiples of 16 bytes by the host-side layout)
@@ -563,7 +564,8 @@ __global__ void __launch_bounds__(1024, 1)
         s_act[a0] = (uint8_t)act0;
         if (has1) s_act[a1] = (uint8_t)act1;
       }
-      if (p.obs != nullptr) obs_k = p.obs + (long long)(k % p.obs_ring) * p.obs_slot_stride;
+      if (p.obs != nullptr) obs_k = p.obs + (long long)obs_slot * p.obs_slot_stride;
+      if (++obs_slot == p.obs_ring) obs_slot = 0;
     }
     team_sync<TEAM>(bar_id);
 
