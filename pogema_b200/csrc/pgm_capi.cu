@@ -192,17 +192,17 @@ int compute_plan(pgm_engine* e) {
   // and 1 x 1024).  The dense cell->agent grid is used when it reaches that residency (one LDS per
   // lookup), otherwise the tile buckets (memory ~ agents instead of cells).
   const int want = std::max(1, std::min(per_sm, std::max(2, 2048 / pow2_ceil(A))));
-  Layout dense, hash, *use = nullptr;  // `hash` = the tile-bucket layout
+  Layout dense, buckets, *use = nullptr;
   const bool ok_d = make_layout(e, 0, want, &dense);
-  const bool ok_h = make_layout(e, 1, want, &hash);
+  const bool ok_h = make_layout(e, 1, want, &buckets);
   const int res_d = ok_d ? std::min(want, smem_max / dense.team_smem) : 0;
-  const int res_h = ok_h ? std::min(want, smem_max / hash.team_smem) : 0;
+  const int res_h = ok_h ? std::min(want, smem_max / buckets.team_smem) : 0;
   int force = -1;
   if (const char* v = getenv("PGM_OCC")) force = atoi(v);  // tuning knob: 0 dense grid, 1 tile buckets
   if (force == 0 && ok_d) use = &dense;
-  else if (force == 1 && ok_h) use = &hash;
+  else if (force == 1 && ok_h) use = &buckets;
   else if (ok_d && res_d >= res_h) use = &dense;
-  else if (ok_h) use = &hash;
+  else if (ok_h) use = &buckets;
   Layout huge;
   if (!use && make_layout(e, 1, 1, &huge, true)) use = &huge;  // bitmaps too large: obstacles stay in global memory
   if (!use)

@@ -1,6 +1,11 @@
-"""Prototype of the parallel (closed-form) move resolution used by the CUDA kernel, fuzzed vs the oracle."""
+"""Prototype of the parallel (closed-form) move resolution used by the CUDA kernel (phase 2 of
+pgm_step_kernel), fuzzed against the sequential oracle.  Development record: this is how the closed
+forms in DESIGN.md section 3 were validated before they were written in CUDA.
+
+    python tools/prototypes/closed_form.py 4000
+"""
 import sys, random
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 import numpy as np
 from oracle.pogema_oracle import GridConfig, Pogema, MOVES
 

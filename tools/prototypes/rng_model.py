@@ -1,3 +1,9 @@
+"""Pure-Python model of the numpy Generator pieces the path consumes (SeedSequence, PCG64, buffered
+uint32, Lemire bounded integers, random_interval, binomial n=1), checked against the installed numpy.
+Development record for pogema_b200/csrc/pgm_rng.h.
+
+    python tools/prototypes/rng_model.py
+"""
 import numpy as np
 M64=(1<<64)-1; M128=(1<<128)-1; M32=(1<<32)-1
 MULT=0x2360ed051fc65da44385df649fccf645
