@@ -483,6 +483,28 @@ __global__ void __launch_bounds__(1024, 1)
     mbar_expect_tx(s_bar, bytes);
     bulk_g2s(base + p.off_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
   }
+  // per-step fills: bitmaps to zero, occupancy structure to "empty" (both regions are padded to multiples of
+  // 16 bytes by the host-side layout).  The first step's fills do not depend on the previous launch.
+  auto step_fills = [&]() {
+    const int abits_vec = (p.PH * WPR + 1 + 3) >> 2;
+    uint4* a4 = reinterpret_cast<uint4*>(s_abits);
+    for (int w = tid; w < abits_vec; w += TEAM) a4[w] = make_uint4(0u, 0u, 0u, 0u);
+    if (OP == OP_STEP) {
+      // dense: every cell = OCC_NONE; buckets: every tile head = empty (both are all-ones fills)
+      const int occ_vec = (OCC == 0) ? ((p.PH * PW * 2 + 4 + 15) >> 4) : ((p.occ_tiles + 3) >> 2);
+      uint4* o4 = reinterpret_cast<uint4*>(occ.dense);
+      for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      if (OCC == 1 && p.off_pbits != p.off_abits) {
+        uint4* p4 = reinterpret_cast<uint4*>(occ.pbits);
+        for (int w = tid; w < abits_vec; w += TEAM) p4[w] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (tid == 0) {
+        s_cnt[0] = 0;
+        s_cnt[1] = 0;
+      }
+    }
+  };
+  step_fills();
   // ---- phase 0b: mutable state of this instance (two agents per thread in flight)
   PGM_STAMP(1);
   pdl_wait();
@@ -527,26 +549,6 @@ __global__ void __launch_bounds__(1024, 1)
   int obs_slot = 0;  // k % obs_ring without a division per step
 #pragma unroll 1
   for (int k = 0; k < num_steps; ++k) {
-    // ---- per-step fills (both regions are padded to multiples of 16 bytes by the host-side layout)
-    {
-      const int abits_vec = (p.PH * WPR + 1 + 3) >> 2;
-      uint4* a4 = reinterpret_cast<uint4*>(s_abits);
-      for (int w = tid; w < abits_vec; w += TEAM) a4[w] = make_uint4(0u, 0u, 0u, 0u);
-      if (OP == OP_STEP) {
-        // dense: every cell = OCC_NONE; buckets: every tile head = empty (both are all-ones fills)
-        const int occ_vec = (OCC == 0) ? ((p.PH * PW * 2 + 4 + 15) >> 4) : ((p.occ_tiles + 3) >> 2);
-        uint4* o4 = reinterpret_cast<uint4*>(occ.dense);
-        for (int w = tid; w < occ_vec; w += TEAM) o4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (OCC == 1 && p.off_pbits != p.off_abits) {
-          uint4* p4 = reinterpret_cast<uint4*>(occ.pbits);
-          for (int w = tid; w < abits_vec; w += TEAM) p4[w] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (tid == 0) {
-          s_cnt[0] = 0;
-          s_cnt[1] = 0;
-        }
-      }
-    }
     uint8_t* obs_k = p.obs;
     if (OP == OP_STEP) {
       // actions of step k
@@ -805,7 +807,10 @@ __global__ void __launch_bounds__(1024, 1)
       emit_observations<TEAM, RT>(p, dbg, obs_k, n, tid, bar_id, s_obst, s_abits, s_stage, s_npos, s_tgt);
       if (OP == OP_OBSERVE && p.mask != nullptr && tid == 0) p.regen_flag[n] = 0;
     }
-    if (k + 1 < num_steps) team_sync<TEAM>(bar_id);  // stage (aliasing occ) and s_act are rewritten next
+    if (k + 1 < num_steps) {
+      team_sync<TEAM>(bar_id);  // stage (aliasing occ) and s_act are rewritten next
+      step_fills();
+    }
   }
 }
 
