@@ -331,6 +331,15 @@ __device__ __forceinline__ void agent_bits_static(const uint32_t* s_obst, const 
   do {                                      \
     if (dbg != nullptr) dbg[(k)] = clock64(); \
   } while (0)
+// wall-clock (globaltimer, ns) stamps: comparable across SMs
+#define PGM_STAMP_NS(k)                                              \
+  do {                                                               \
+    if (dbg != nullptr) {                                            \
+      unsigned long long _t;                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));       \
+      dbg[(k)] = (long long)_t;                                      \
+    }                                                                \
+  } while (0)
 
 template <int TEAM, int RT>
 __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* dbg, uint8_t* obs, int n, int tid,
@@ -413,6 +422,7 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* 
     if (g0 + p.batch_agents < p.A) team_sync<TEAM>(bar_id);
   }
   PGM_STAMP(8);
+  PGM_STAMP_NS(11);
 }
 
 // ------------------------------------------------------------------------- //
@@ -475,6 +485,7 @@ __global__ void __launch_bounds__(1024, 1)
   // this grid to complete and flush, so there is no cross-launch race on any buffer.
   pdl_trigger();
   PGM_STAMP(0);
+  PGM_STAMP_NS(9);
   // ---- phase 0a (independent of the previous launch): obstacle map by bulk copy
   if (!OG && tid == 0) {
     mbar_init(s_bar, 1);
@@ -509,6 +520,7 @@ __global__ void __launch_bounds__(1024, 1)
   PGM_STAMP(1);
   pdl_wait();
   PGM_STAMP(2);
+  PGM_STAMP_NS(10);
   int step_idx = 0;
   int m_acc0 = 0, m_acc1 = 0, m_acc2 = 0;
   if (OP == OP_STEP) {

@@ -36,3 +36,13 @@ for k in range(1, 9):
     print("%-16s mean %8.0f  p50 %8.0f  p95 %8.0f  max %8.0f cycles" % (names[k], dt.mean(), np.percentile(dt, 50), np.percentile(dt, 95), dt.max()))
 tot = d[:, 8] - d[:, 0]
 print("%-16s mean %8.0f  p50 %8.0f  p95 %8.0f  max %8.0f cycles" % ("total", tot.mean(), np.percentile(tot, 50), np.percentile(tot, 95), tot.max()))
+
+# wall-clock view (globaltimer ns) of the LAST launch: when do instances start / pass the dependency wait / finish
+t9, t10, t11 = d[:, 9], d[:, 10], d[:, 11]
+t0 = t9.min()
+print("launch wall clock (us): first CTA start 0.00 | last CTA start %.2f | dependency wait passed: first %.2f last %.2f |"
+      " finish: first %.2f  p50 %.2f  p95 %.2f  last %.2f" % ((t9.max() - t0) / 1e3, (t10.min() - t0) / 1e3, (t10.max() - t0) / 1e3,
+                                                         (t11.min() - t0) / 1e3, (np.percentile(t11, 50) - t0) / 1e3,
+                                                         (np.percentile(t11, 95) - t0) / 1e3, (t11.max() - t0) / 1e3))
+work = (t11 - t10) / 1e3
+print("per-instance work after the wait (us): mean %.2f p50 %.2f p95 %.2f max %.2f" % (work.mean(), np.percentile(work, 50), np.percentile(work, 95), work.max()))
