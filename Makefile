@@ -3,11 +3,12 @@ NVCC ?= nvcc
 CXX ?= g++
 CC ?= gcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O3,-Wall
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xfatbin=-compress-all -Xcompiler -fPIC,-O3,-Wall
 CSRC := pogema_b200/csrc
 BUILD := build
 LIB := pogema_b200/_lib/libpgm_b200.so
-CU := pgm_capi pgm_devgen pgm_inst_step_priority pgm_inst_step_block_both pgm_inst_step_soft pgm_inst_observe pgm_inst_reset
+INST := step_priority step_block_both step_soft observe reset
+CU := pgm_capi pgm_devgen $(foreach i,$(INST),pgm_inst_$(i)_g0 pgm_inst_$(i)_g1)
 OBJS := $(addprefix $(BUILD)/,$(addsuffix .o,$(CU))) $(BUILD)/pgm_gen.o
 HDRS := $(CSRC)/pgm_devgen.h $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h include/pgm_b200.h
 

@@ -260,12 +260,18 @@ int compute_plan(pgm_engine* e) {
 int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
   LaunchDims d{e->team, static_radius(e->cfg.obs_radius), e->grid, e->cta_threads, e->smem_cta, e->cfg.device,
                e->use_pdl ? 1 : 0, e->occ_mode, e->obst_global};
+  // huge maps (obstacles in global memory) only have the generic and the r=5 variants
+  if (d.og && d.rt != 5) d.rt = 0;
+  const int g = d.og ? (d.rt == 5 ? 1 : 0) : radius_group(d.rt);
   int err;
-  if (op == OP_OBSERVE) err = launch_observe(d, a, s);
-  else if (op == OP_RESET) err = launch_reset(d, a, s);
-  else if (e->cfg.collision_system == PGM_COLLISION_PRIORITY) err = launch_step_priority(d, a, s);
-  else if (e->cfg.collision_system == PGM_COLLISION_BLOCK_BOTH) err = launch_step_block_both(d, a, s);
-  else err = launch_step_soft(d, a, s);
+  if (op == OP_OBSERVE) err = g ? launch_observe_g1(d, a, s) : launch_observe_g0(d, a, s);
+  else if (op == OP_RESET) err = g ? launch_reset_g1(d, a, s) : launch_reset_g0(d, a, s);
+  else if (e->cfg.collision_system == PGM_COLLISION_PRIORITY)
+    err = g ? launch_step_priority_g1(d, a, s) : launch_step_priority_g0(d, a, s);
+  else if (e->cfg.collision_system == PGM_COLLISION_BLOCK_BOTH)
+    err = g ? launch_step_block_both_g1(d, a, s) : launch_step_block_both_g0(d, a, s);
+  else
+    err = g ? launch_step_soft_g1(d, a, s) : launch_step_soft_g0(d, a, s);
   if (err != 0)
     return fail(PGM_ERR_CUDA, "kernel launch failed: %s (grid %d, block %d, smem %d)",
                 cudaGetErrorString((cudaError_t)err), d.grid, d.block, d.smem);

@@ -1,0 +1,5 @@
+// pgm_inst_step_block_both_g0.cu - instantiates pgm_step_kernel<*, 1, OP_STEP, radius group 0, *> (see pgm_launch.cuh)
+#include "pgm_launch.cuh"
+namespace pgm {
+int launch_step_block_both_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s) { return launch_variant<1, OP_STEP, 0>(d, a, s); }
+}  // namespace pgm

@@ -37,58 +37,74 @@ int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   return (int)cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-template <int TEAM, int COLL, int OP, int OCC>
+// Radii with a compile-time specialisation are split in two groups (RTG) so that the variants of one
+// (COLL, OP) pair compile in two translation units: group 0 = generic + r 1..3, group 1 = r 4..7.
+template <int TEAM, int COLL, int OP, int OCC, int RTG>
 int launch_rt_occ(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
-  switch (d.rt) {
-    case 3: return launch_exact<TEAM, COLL, OP, 3, OCC>(d, a, s);
-    case 5: return launch_exact<TEAM, COLL, OP, 5, OCC>(d, a, s);
-    case 7: return launch_exact<TEAM, COLL, OP, 7, OCC>(d, a, s);
-    default: return launch_exact<TEAM, COLL, OP, 0, OCC>(d, a, s);
+  if constexpr (RTG == 0) {
+    switch (d.rt) {
+      case 1: return launch_exact<TEAM, COLL, OP, 1, OCC>(d, a, s);
+      case 2: return launch_exact<TEAM, COLL, OP, 2, OCC>(d, a, s);
+      case 3: return launch_exact<TEAM, COLL, OP, 3, OCC>(d, a, s);
+      default: return launch_exact<TEAM, COLL, OP, 0, OCC>(d, a, s);
+    }
+  } else {
+    switch (d.rt) {
+      case 4: return launch_exact<TEAM, COLL, OP, 4, OCC>(d, a, s);
+      case 5: return launch_exact<TEAM, COLL, OP, 5, OCC>(d, a, s);
+      case 6: return launch_exact<TEAM, COLL, OP, 6, OCC>(d, a, s);
+      default: return launch_exact<TEAM, COLL, OP, 7, OCC>(d, a, s);
+    }
   }
 }
 
-template <int TEAM, int COLL, int OP>
+template <int TEAM, int COLL, int OP, int RTG>
 int launch_rt(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   // the occupancy structure only exists in the step path
   if constexpr (OP == OP_STEP) {
-    if (d.occ == 1) return launch_rt_occ<TEAM, COLL, OP, 1>(d, a, s);
+    if (d.occ == 1) return launch_rt_occ<TEAM, COLL, OP, 1, RTG>(d, a, s);
   }
-  return launch_rt_occ<TEAM, COLL, OP, 0>(d, a, s);
+  return launch_rt_occ<TEAM, COLL, OP, 0, RTG>(d, a, s);
 }
 
 // obstacle bitmap in global memory (huge maps): 1024-thread teams, tile buckets only
-template <int COLL, int OP>
+template <int COLL, int OP, int RTG>
 int launch_og(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   constexpr int OCC = (OP == OP_STEP) ? 1 : 0;
-  switch (d.rt) {
-    case 3: return launch_exact<1024, COLL, OP, 3, OCC, 1>(d, a, s);
-    case 5: return launch_exact<1024, COLL, OP, 5, OCC, 1>(d, a, s);
-    case 7: return launch_exact<1024, COLL, OP, 7, OCC, 1>(d, a, s);
-    default: return launch_exact<1024, COLL, OP, 0, OCC, 1>(d, a, s);
+  if constexpr (RTG == 0) {
+    return launch_exact<1024, COLL, OP, 0, OCC, 1>(d, a, s);  // huge maps: generic radius path only
+  } else {
+    return launch_exact<1024, COLL, OP, 5, OCC, 1>(d, a, s);  // ... and the default radius 5
   }
 }
 
-template <int COLL, int OP>
+template <int COLL, int OP, int RTG>
 int launch_variant(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
-  if (d.og) return launch_og<COLL, OP>(d, a, s);
+  if (d.og) return launch_og<COLL, OP, RTG>(d, a, s);
   switch (d.team) {
-    case 32: return launch_rt<32, COLL, OP>(d, a, s);
-    case 64: return launch_rt<64, COLL, OP>(d, a, s);
-    case 128: return launch_rt<128, COLL, OP>(d, a, s);
-    case 256: return launch_rt<256, COLL, OP>(d, a, s);
-    case 512: return launch_rt<512, COLL, OP>(d, a, s);
-    default: return launch_rt<1024, COLL, OP>(d, a, s);
+    case 32: return launch_rt<32, COLL, OP, RTG>(d, a, s);
+    case 64: return launch_rt<64, COLL, OP, RTG>(d, a, s);
+    case 128: return launch_rt<128, COLL, OP, RTG>(d, a, s);
+    case 256: return launch_rt<256, COLL, OP, RTG>(d, a, s);
+    case 512: return launch_rt<512, COLL, OP, RTG>(d, a, s);
+    default: return launch_rt<1024, COLL, OP, RTG>(d, a, s);
   }
 }
 
-// defined in pgm_inst_*.cu
-int launch_step_priority(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
-int launch_step_block_both(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
-int launch_step_soft(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
-int launch_observe(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
-int launch_reset(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+// defined in pgm_inst_*.cu (suffix = radius group)
+int launch_step_priority_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_step_priority_g1(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_step_block_both_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_step_block_both_g1(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_step_soft_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_step_soft_g1(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_observe_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_observe_g1(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_reset_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_reset_g1(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
 
-// radii with a compile-time specialisation
-inline int static_radius(int r) { return (r == 3 || r == 5 || r == 7) ? r : 0; }
+// radii with a compile-time specialisation (1..7); every other radius runs the generic path
+inline int static_radius(int r) { return (r >= 1 && r <= 7) ? r : 0; }
+inline int radius_group(int rt) { return rt >= 4 ? 1 : 0; }
 
 }  // namespace pgm
