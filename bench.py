@@ -374,6 +374,29 @@ def run_cuda(args):
     h2d = N * A
     d2h = env.engine.obs_bytes + N * A * 4 + 2 * N * A
 
+    # same call with the bit-packed observation format (48 B instead of 363 B per agent over PCIe)
+    e2e_bits = None
+    if world == 1:
+        envb = BatchedPogema(gc, num_envs=N, device=dev, seeds=seeds, auto_reset=True, obs_format="bits")
+        envb.reset()
+        hb_obs = torch.empty(envb.engine.obs_shape(), dtype=torch.int32).pin_memory()
+
+        def host_step_bits(i):
+            envb.engine.step_host(h_act[i % 4].numpy(), hb_obs.numpy(), h_rew.numpy(), h_term.numpy(), h_trunc.numpy(), sptr)
+
+        for i in range(3):
+            host_step_bits(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            host_step_bits(i)
+        torch.cuda.synchronize()
+        tb = time.perf_counter() - t0
+        e2e_bits = {"value": N * A * e2e_steps / tb, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": envb.engine.obs_bytes + N * A * 4 + 2 * N * A, "steps": e2e_steps,
+                    "api": "pgm_step_host with obs_format=bits (uint32 [N,A,12], bit k = element k of the uint8 layout)"}
+        envb.close()
+
     if rank == 0:
         r = WORKLOAD["obs_radius"]
         P = WORKLOAD["size"] + 2 * r
@@ -401,6 +424,7 @@ def run_cuda(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "closed_loop": closed_loop,
+            "e2e_bits": e2e_bits,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
