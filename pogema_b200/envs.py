@@ -177,9 +177,28 @@ class Pogema(_Base):
         self._initial_xy = None
         full = grid_config.obs_radius * 2 + 1
         self.action_space = Discrete(len(grid_config.MOVES))
-        self.observation_space = Box(0.0, 1.0, shape=(3, full, full), dtype=np.float32)
+        self.observation_space = self._make_observation_space(grid_config, full)
         self._multi_action_sampler = ActionsSampler(self.action_space.n, seed=grid_config.seed)
         self._elapsed_steps = None
+
+    @staticmethod
+    def _make_observation_space(gc, full):
+        """upstream envs.py :: Pogema.__init__: Box(3, D, D) for 'default', Dict spaces for POMAPF / MAPF."""
+        if gc.observation_type == 'default':
+            return Box(0.0, 1.0, shape=(3, full, full), dtype=np.float32)
+        spaces = dict(obstacles=Box(0.0, 1.0, shape=(full, full), dtype=np.float32),
+                      agents=Box(0.0, 1.0, shape=(full, full), dtype=np.float32),
+                      xy=Box(low=-1024, high=1024, shape=(2,), dtype=int),
+                      target_xy=Box(low=-1024, high=1024, shape=(2,), dtype=int))
+        if gc.observation_type == 'MAPF':
+            h, w = gc.map_shape()
+            r = gc.obs_radius
+            spaces.update(global_obstacles=Box(0.0, 1.0, shape=(h + 2 * r, w + 2 * r), dtype=np.float32),
+                          global_xy=Box(low=-1024, high=1024, shape=(2,), dtype=int),
+                          global_target_xy=Box(low=-1024, high=1024, shape=(2,), dtype=int))
+        if gymnasium is not None:
+            return gymnasium.spaces.Dict(**spaces)
+        return spaces
 
     # -- helpers --------------------------------------------------------- #
     def _ensure_engine(self):
