@@ -64,12 +64,14 @@ enum {
   PGM_STATE_OBSTACLES = 4, /* uint8 [N][H][W] unpadded (host copy only)                          */
   PGM_STATE_WAS_ON_GOAL = 5,/* uint8 [N][A]  upstream envs.py :: Pogema.was_on_goal (last step)  */
   PGM_STATE_EPISODE_DONE = 6,/* uint8 [N]    all(terminated) or all(truncated) on the last step  */
-  PGM_STATE_METRICS = 7    /* int32 [N][4] raw counters of the last finished episode, from which
+  PGM_STATE_METRICS = 7,   /* int32 [N][4] raw counters of the last finished episode, from which
                               upstream wrappers/metrics.py values follow:
                               [0] sum of was_on_goal over the episode  (ISR = [0]/A, CSR = [0]==A,
                                   avg_throughput = [0]/max_episode_steps)
                               [1] sum of per-agent solve steps         (ep_length = [1]/A + 1)
                               [2] episode length in steps  [3] agents on goal at the last step     */
+  PGM_STATE_SEEDS = 8      /* uint64 [N] seed each instance's current task was built from (advances
+                              under auto_reset=2)                                                  */
 };
 
 typedef struct pgm_config {

@@ -186,6 +186,10 @@ class BatchedPogema:
         r = self.grid_config.obs_radius
         return torch.stack(((w & 0x7FFF) - r, ((w >> 16) & 0xFFFF) - r), dim=-1)
 
+    def current_seeds(self) -> np.ndarray:
+        """uint64 [N]: the seed each instance's current task was built from (advances with auto_reset='reseed')."""
+        return self.engine.get_state(nat.STATE_SEEDS, self._stream())
+
     def get_obstacles(self) -> np.ndarray:
         """uint8 [N, H, W] unpadded obstacle maps (host array)."""
         return self.engine.get_state(nat.STATE_OBSTACLES)

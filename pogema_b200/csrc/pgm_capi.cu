@@ -952,6 +952,12 @@ int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, voi
       CUDA_TRY(cudaStreamSynchronize(s));
       return PGM_OK;
     }
+    case PGM_STATE_SEEDS: {
+      if (need(N * 8)) return PGM_ERR_INVALID;
+      CUDA_TRY(cudaMemcpyAsync(dst, e->d_cur_seeds, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      return PGM_OK;
+    }
     case PGM_STATE_OBSTACLES: {
       const int64_t H = e->cfg.height, W = e->cfg.width;
       if (need(N * H * W)) return PGM_ERR_INVALID;

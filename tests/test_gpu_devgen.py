@@ -140,6 +140,7 @@ def test_auto_reset_with_new_seeds_matches_oracle(ot, coll):
                 episodes += 1
             assert np.array_equal(o[k], np.stack(ro).astype(np.uint8)), (t, k)
     assert episodes >= 25
+    assert env.current_seeds().tolist() == cur
     env.check_errors()
     with pytest.raises(Exception):
         env.rollout(torch.zeros((4, len(seeds), kw["num_agents"]), dtype=torch.uint8, device="cuda"))
