@@ -14,6 +14,7 @@ struct DevGenArgs {
   const uint64_t* seeds;   // device [count] (direct mode)
   const uint64_t* cur_seeds;  // regeneration mode: seed of instance n = cur_seeds[n]
   int slots;               // scratch slots = warps of the launch; warp w handles entries w, w+slots, ...
+  int smem_labels;         // set by launch_devgen: component labelling runs in shared memory (small maps)
   int* err_flag;           // regeneration mode: sticky engine error flag (bit 2: task could not be rebuilt)
   int H, W, A, r, lifelong;
   const uint8_t* map;      // optional device map [H][W] shared by all instances
