@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer passes over small runs of every collision system / on_target mode (GPU box).
 set -x
-for tool in memcheck racecheck synccheck; do
+for tool in memcheck racecheck synccheck initcheck; do
   for mode in "priority finish" "block_both nothing" "soft restart"; do
     set -- $mode
     compute-sanitizer --tool $tool --error-exitcode 9 python tools/quick_bench.py --n 48 --size 12 --agents 20 --r 3 \
@@ -11,4 +11,6 @@ for tool in memcheck racecheck synccheck; do
   done
 done
 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/quick_bench.py --n 48 --size 12 --agents 20 --r 4 --coll soft --ot restart --steps 32 --many 8 --max-steps 5 > gpurun_out/san_memcheck_many.log 2>&1; echo "memcheck many exit=$?"; tail -2 gpurun_out/san_memcheck_many.log
+compute-sanitizer --tool memcheck --error-exitcode 9 python tools/quick_bench.py --n 6 --size 300 --agents 40 --r 5 --coll soft --ot restart --steps 4 --max-steps 5 > gpurun_out/san_memcheck_buckets.log 2>&1; echo "memcheck tile-buckets exit=$?"; tail -2 gpurun_out/san_memcheck_buckets.log
+compute-sanitizer --tool racecheck --error-exitcode 9 python tools/quick_bench.py --n 6 --size 300 --agents 40 --r 5 --coll priority --ot finish --steps 4 --max-steps 5 > gpurun_out/san_racecheck_buckets.log 2>&1; echo "racecheck tile-buckets exit=$?"; tail -2 gpurun_out/san_racecheck_buckets.log
 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/quick_bench.py --n 24 --size 40 --agents 300 --r 5 --coll priority --ot finish --steps 4 --max-steps 5 > gpurun_out/san_racecheck_team.log 2>&1; echo "racecheck big-team exit=$?"; tail -2 gpurun_out/san_racecheck_team.log
