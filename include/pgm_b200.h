@@ -51,7 +51,8 @@ enum { PGM_ON_TARGET_FINISH = 0, PGM_ON_TARGET_NOTHING = 1, PGM_ON_TARGET_RESTAR
 enum {
   PGM_OBS_U8 = 0,  /* uint8 [N][A][3][D][D], values 0/1, channels obstacles/agents/target
                       (upstream envs.py :: _get_agents_obs; float32 upstream, same values)       */
-  PGM_OBS_BITS = 1 /* uint32 [N][A][ceil(3*D*D/32)], bit k = element k of the uint8 layout       */
+  PGM_OBS_BITS = 1,/* uint32 [N][A][ceil(3*D*D/32)], bit k = element k of the uint8 layout       */
+  PGM_OBS_F32 = 2  /* float32 [N][A][3][D][D], values 0.0/1.0 - the reference's own dtype         */
 };
 /* pgm_get_state / pgm_state_ptr selectors */
 enum {

@@ -29,7 +29,8 @@ class BatchedPogema:
     (default ``seeds[k] = (grid_config.seed or 0) + k``).
 
     ``reset() -> obs``; ``step(actions) -> obs, rewards, terminated, truncated``:
-      obs         uint8  [N, A, 3, D, D]   (or uint32 [N, A, ceil(3*D*D/32)] with obs_format='bits')
+      obs         uint8  [N, A, 3, D, D]   (uint32 [N, A, ceil(3*D*D/32)] with obs_format='bits',
+                                          float32 [N, A, 3, D, D] - the reference's dtype - with obs_format='f32')
       rewards     float32 [N, A]
       terminated  bool   [N, A]
       truncated   bool   [N, A]
@@ -86,7 +87,7 @@ class BatchedPogema:
 
     def _alloc_obs(self) -> torch.Tensor:
         e = self.engine
-        dtype = torch.int32 if e.obs_format == "bits" else torch.uint8
+        dtype = {"bits": torch.int32, "f32": torch.float32}.get(e.obs_format, torch.uint8)
         return torch.empty(e.obs_shape(), dtype=dtype, device=self.device)
 
     def new_obs_buffer(self) -> torch.Tensor:

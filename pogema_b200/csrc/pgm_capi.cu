@@ -556,7 +556,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
   if (cfg->collision_system < 0 || cfg->collision_system > 2) return fail(PGM_ERR_INVALID, "bad collision_system");
   if (cfg->on_target < 0 || cfg->on_target > 2) return fail(PGM_ERR_INVALID, "bad on_target");
   if (cfg->auto_reset < 0 || cfg->auto_reset > 2) return fail(PGM_ERR_INVALID, "auto_reset must be 0, 1 or 2");
-  if (cfg->obs_format < 0 || cfg->obs_format > 1) return fail(PGM_ERR_INVALID, "bad obs_format");
+  if (cfg->obs_format < 0 || cfg->obs_format > 2) return fail(PGM_ERR_INVALID, "bad obs_format");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev)
@@ -582,7 +582,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
     e->obs_inst_stride = A * (e->stage_bpa / 8);
   } else {
     e->stage_bpa = e->bits_per_agent;
-    e->obs_inst_stride = A * e->bits_per_agent;
+    e->obs_inst_stride = A * e->bits_per_agent * (cfg->obs_format == PGM_OBS_F32 ? 4 : 1);
   }
   e->obs_bytes = N * e->obs_inst_stride;
   e->cells_stride = (int64_t)cfg->height * cfg->width;

@@ -41,7 +41,7 @@ struct StepArgs {
   int obst_stride;      // uint32 words per instance (multiple of 4, >= PH*WPR + 1)
   int bits_per_agent;   // 3*D*D
   int stage_bpa;        // stage bits per agent: bits_per_agent (U8) or rounded up to 32 (BITS)
-  int obs_format;       // 0 u8, 1 bits
+  int obs_format;       // 0 u8, 1 bits, 2 float32
   int max_steps, auto_reset;
   int on_target;        // 0 finish, 1 nothing, 2 restart
   int batch_agents;     // agents per observation batch (stage capacity)
@@ -380,6 +380,30 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* 
       const int wpa = sbpa >> 5;
       uint32_t* out = reinterpret_cast<uint32_t*>(obs + (long long)n * p.obs_inst_stride) + (long long)g0 * wpa;
       for (int w = tid; w < gcount * wpa; w += TEAM) __stcs(out + w, stage[w]);
+    } else if (p.obs_format == 2) {
+      // float32 0.0 / 1.0 (the reference's observation dtype): one stream bit -> one float, 16-byte stores
+      float* out = reinterpret_cast<float*>(obs + (long long)n * p.obs_inst_stride) + (long long)g0 * bpa;
+      const int nfl = gcount * bpa;
+      int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u) >> 2);
+      head = min(head, nfl);
+      const int chunks = (nfl - head) >> 2;
+      uint4* out16 = reinterpret_cast<uint4*>(out + head);
+      for (int c = tid; c < chunks; c += TEAM) {
+        const uint32_t bit = (uint32_t)head + ((uint32_t)c << 2);
+        const uint32_t w = bit >> 5, sh = bit & 31u;
+        const uint32_t v = __funnelshift_r(stage[w], stage[w + 1], sh);
+        uint4 o;
+        o.x = (v & 1u) ? 0x3F800000u : 0u;
+        o.y = (v & 2u) ? 0x3F800000u : 0u;
+        o.z = (v & 4u) ? 0x3F800000u : 0u;
+        o.w = (v & 8u) ? 0x3F800000u : 0u;
+        __stcs(out16 + c, o);
+      }
+      const int tail0 = head + (chunks << 2);
+      for (int b = tid; b < head + (nfl - tail0); b += TEAM) {
+        const int bb = b < head ? b : tail0 + (b - head);
+        out[bb] = ((stage[bb >> 5] >> (bb & 31)) & 1u) ? 1.0f : 0.0f;
+      }
     } else {
       uint8_t* out = obs + (long long)n * p.obs_inst_stride + (long long)g0 * bpa;
       const int nbytes = gcount * bpa;

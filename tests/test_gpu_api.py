@@ -90,6 +90,24 @@ def test_bits_format_equals_u8():
             ob = b.step(act)[0]
 
 
+def test_f32_format_equals_u8():
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    for r, agents in ((2, 7), (5, 20), (9, 5)):
+        gc = GridConfig(size=16, density=0.3, num_agents=agents, obs_radius=r, max_episode_steps=16,
+                        collision_system="priority", on_target="finish", seed=2)
+        a = BatchedPogema(gc, num_envs=5, auto_reset=True)
+        b = BatchedPogema(gc, num_envs=5, auto_reset=True, obs_format="f32")
+        oa, ob = a.reset(), b.reset()
+        assert ob.dtype == torch.float32 and ob.shape == oa.shape
+        g = torch.Generator(device="cuda").manual_seed(0)
+        for t in range(30):
+            assert torch.equal(ob, oa.float())
+            act = a.sample_actions(g)
+            oa = a.step(act)[0]
+            ob = b.step(act)[0]
+
+
 def test_checkpoint_resume_and_host_step():
     import torch
     from pogema_b200 import BatchedPogema, GridConfig
