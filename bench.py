@@ -416,7 +416,7 @@ def run_cuda(args):
                        "steps_per_launch": SPL,
                        "plan": env.engine.plan(), "parallelism": f"instances sharded over {world} GPU(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000_GBps": achieved / 8000.0,
                          "algorithmic_bytes_per_agent_step": bpa, "kernel": "pgm_step_kernel (%d step(s) per launch)" % SPL,
                          "algorithmic_bytes_per_launch": N * A * bpa * SPL},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

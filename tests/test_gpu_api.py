@@ -244,3 +244,45 @@ def test_dict_observation_types(kind):
         o = env.step(a)[0]
         ro = ref.step(a)[0]
         same(o, ro)
+
+
+@pytest.mark.parametrize("ot", ["finish", "restart", "nothing"])
+def test_interleaved_api_calls_equal_plain_stepping(ot):
+    """step / rollout / observe / checkpoint-restore / reset interleaved at random must leave the engine
+    in exactly the state plain stepping produces."""
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    gc = GridConfig(size=12, density=0.2, num_agents=14, obs_radius=3, max_episode_steps=11,
+                    collision_system="soft", on_target=ot, seed=0)
+    a = BatchedPogema(gc, num_envs=9, auto_reset=True)
+    b = BatchedPogema(gc, num_envs=9, auto_reset=True)
+    a.reset(), b.reset()
+    rng = np.random.default_rng(5)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    saved = None
+    for it in range(60):
+        op = rng.integers(0, 6)
+        if op <= 1:
+            act = a.sample_actions(g)
+            ra, rb = a.step(act), b.step(act)
+            assert all(torch.equal(x, y) for x, y in zip(ra, rb))
+        elif op == 2:
+            K = int(rng.integers(1, 9))
+            acts = torch.stack([a.sample_actions(g) for _ in range(K)])
+            obs, rew, term, trunc = a.rollout(acts)
+            for k in range(K):
+                o, r, te, tr = b.step(acts[k])
+                assert torch.equal(obs[k], o) and torch.equal(rew[k], r) and torch.equal(term[k], te) and torch.equal(trunc[k], tr)
+        elif op == 3:
+            assert torch.equal(a.observe(), b.observe())
+        elif op == 4:
+            if saved is None or rng.random() < 0.5:
+                saved = (a.state_dict(), b.state_dict())
+            else:
+                a.load_state_dict(saved[0]), b.load_state_dict(saved[1])
+        else:
+            assert torch.equal(a.reset(), b.reset())
+        assert torch.equal(a._state(), b._state()) and torch.equal(a.elapsed_steps, b.elapsed_steps)
+        assert np.array_equal(a.engine.checkpoint(), b.engine.checkpoint())
+    ma, mb = a.metrics(), b.metrics()
+    assert all(np.array_equal(ma[k], mb[k]) for k in ma)
