@@ -1,18 +1,23 @@
 // pgm_kernels.cuh - the fused POGEMA step kernel for sm_100a.
 //
 // One TEAM of threads (a warp, or 64..1024 threads on a named barrier) owns one
-// instance for the whole step; everything an instance needs lives in that
+// instance for the whole launch; everything an instance needs lives in that
 // team's slice of shared memory:
 //
-//   obst   bit-packed PADDED obstacle map  (cp.async.bulk global->shared, mbarrier)
-//   occ    uint16 cell -> agent index grid (pre-move occupancy, for conflict lookups)
+//   obst   bit-packed PADDED obstacle map  (cp.async.bulk global->shared, mbarrier;
+//          read from global memory instead when two bitmaps do not fit: OG = 1)
+//   occ    pre-move occupancy: dense uint16 cell -> agent grid (OCC = 0) or tile
+//          buckets behind a pre-move bitmap (OCC = 1), for the conflict lookups
 //   abits  bit-packed post-move agent occupancy
 //   stage  the observation bit stream of a batch of agents (aliases occ)
 //
-// Phases: load -> occupancy grid -> move resolution (closed forms of the three
+// A launch advances its instances by num_steps steps (pgm_step: 1, pgm_step_many: K;
+// every team then runs its own timeline without any grid-wide barrier).  Phases of
+// a step: fills + actions -> occupancy -> move resolution (closed forms of the three
 // upstream collision systems, pointer jumping for the dependent chains) ->
 // on_target bookkeeping / time limit / auto reset -> observation bits ->
-// bit->byte expansion with 16-byte streaming stores.
+// bit->byte expansion with 16-byte streaming stores.  OP_OBSERVE / OP_RESET reuse
+// the state load and the observation phases.
 //
 // Upstream symbols restated (pure Python upstream; /root/reference holds only
 // README.md:1-5, so symbols are cited by name - SURVEY.md section 8a):
