@@ -125,6 +125,24 @@ class BatchedPogema:
                          self._stream())
         return obs, self._rewards, self._terminated, self._truncated
 
+    def step_host(self, actions: np.ndarray):
+        """``step`` with HOST buffers (``pgm_step_host``): numpy actions in, numpy obs / rewards / terminated /
+        truncated out (copies host<->device inside the call; page-locked result buffers are reused)."""
+        if not hasattr(self, "_h_out"):
+            e = self.engine
+            odt = {"bits": torch.int32, "f32": torch.float32}.get(e.obs_format, torch.uint8)
+            n, a = self.num_envs, self.num_agents
+            self._h_out = (torch.empty(e.obs_shape(), dtype=odt).pin_memory(),
+                           torch.empty((n, a), dtype=torch.float32).pin_memory(),
+                           torch.empty((n, a), dtype=torch.uint8).pin_memory(),
+                           torch.empty((n, a), dtype=torch.uint8).pin_memory())
+        obs, rew, term, trunc = self._h_out
+        actions = np.ascontiguousarray(actions)
+        if actions.shape != (self.num_envs, self.num_agents):
+            raise ValueError(f"actions must have shape {(self.num_envs, self.num_agents)}")
+        self.engine.step_host(actions, obs.numpy(), rew.numpy(), term.numpy(), trunc.numpy(), self._stream())
+        return obs.numpy(), rew.numpy(), term.numpy().astype(bool), trunc.numpy().astype(bool)
+
     def rollout(self, actions: torch.Tensor, obs_out: Optional[torch.Tensor] = None, compute_obs: bool = True):
         """K consecutive steps in ONE kernel launch (``pgm_step_many``) for actions known in advance.
 

@@ -128,6 +128,9 @@ def test_checkpoint_resume_and_host_step():
     rew = np.empty((n, a), np.float32)
     te = np.empty((n, a), np.uint8)
     tr = np.empty((n, a), np.uint8)
+    o2, r2, te2, tr2 = env.step_host(acts[10].cpu().numpy())          # convenience wrapper, same call
+    assert np.array_equal(o2, first[0][0].cpu().numpy()) and np.array_equal(r2, first[0][1].cpu().numpy())
+    env.load_state_dict(sd)
     for t in range(10, 30):
         env.engine.step_host(acts[t].cpu().numpy(), obs, rew, te, tr)
         o, r, term, trunc = first[t - 10]
