@@ -92,3 +92,10 @@ def test_observation_batches_when_the_stage_does_not_fit():
     assert env.engine.plan()["agents_per_obs_batch"] < 48
     env.close()
     run_both(gc, [4, 5], T=8, auto_reset=True, team=0)
+
+
+def test_maximum_observation_radius():
+    """GridConfig's maximum obs_radius (128): D = 257, 198147 values per agent."""
+    gc = dict(size=6, density=0.1, num_agents=3, obs_radius=128, max_episode_steps=4, collision_system="priority",
+              on_target="restart")
+    run_both(gc, [1, 2], T=6, auto_reset=True, team=0)
