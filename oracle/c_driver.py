@@ -23,7 +23,13 @@ PCG_DTYPE = np.dtype([("state_hi", np.uint64), ("state_lo", np.uint64), ("inc_hi
 
 def load():
     if not os.path.exists(LIB):
-        raise RuntimeError("oracle/liboracle_step.so missing: run `make oracle`")
+        # build the checker on the spot (gcc is part of the image); `make oracle` does the same
+        import subprocess
+        src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "step_oracle.c")
+        try:
+            subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-o", LIB, src, "-lm"], check=True)
+        except Exception as exc:  # pragma: no cover
+            raise RuntimeError("oracle/liboracle_step.so missing and gcc failed: run `make oracle`") from exc
     lib = C.CDLL(LIB)
     lib.orc_run.restype = C.c_longlong
     return lib
