@@ -279,9 +279,13 @@ class Pogema(_Base):
         truncated = [bool(self._h_trunc[0, i]) for i in range(n)]
         self.was_on_goal = [bool(v) for v in self._engine.get_state(nat.STATE_WAS_ON_GOAL)[0]]
         infos = self._get_infos()
+        obs = self._obs_list(self._h_obs)
         if all(truncated) or all(terminated):
             infos[0]['metrics'] = self._episode_metrics()
-        return self._obs_list(self._h_obs), rewards, terminated, truncated, infos
+            if self.grid_config.auto_reset:
+                # upstream integrations/sample_factory.py :: AutoResetWrapper: the returned observation is the reset one
+                obs, _ = self.reset()
+        return obs, rewards, terminated, truncated, infos
 
     def _episode_metrics(self):
         """upstream wrappers/metrics.py values from the raw device counters."""

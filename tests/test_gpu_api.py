@@ -289,3 +289,20 @@ def test_interleaved_api_calls_equal_plain_stepping(ot):
         assert np.array_equal(a.engine.checkpoint(), b.engine.checkpoint())
     ma, mb = a.metrics(), b.metrics()
     assert all(np.array_equal(ma[k], mb[k]) for k in ma)
+
+
+def test_list_env_auto_reset_flag():
+    """GridConfig(auto_reset=True): upstream AutoResetWrapper semantics on the list API."""
+    from pogema_b200 import GridConfig, pogema_v0
+    kw = dict(size=8, density=0.2, num_agents=3, obs_radius=2, max_episode_steps=5, seed=4)
+    env = pogema_v0(GridConfig(auto_reset=True, **kw))
+    ref = orc.pogema_v0(orc.GridConfig(**kw))
+    env.reset()
+    ref.reset()
+    for t in range(17):
+        a = ref.sample_actions()
+        o, r, te, tr, inf = env.step(a)
+        ro, rr, rte, rtr, rinf = ref.step(a)
+        if all(rte) or all(rtr):
+            ro, _ = ref.reset()
+        assert all(np.array_equal(x, y) for x, y in zip(o, ro)) and r == rr and te == rte and tr == rtr
