@@ -43,7 +43,7 @@ def run_both(gc, seeds, T, auto_reset, team, fmt="u8"):
     env.close()
 
 
-@pytest.mark.parametrize("case", range(36))
+@pytest.mark.parametrize("case", range(int(os.environ.get("PGM_FUZZ_CASES", "36"))))
 def test_random_configurations(case, monkeypatch):
     rng = np.random.default_rng(1000 + case)
     size = int(rng.integers(4, 36))
