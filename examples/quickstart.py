@@ -1,0 +1,44 @@
+"""Quick start: the three ways to drive the engine (needs a CUDA device and a built libpgm_b200.so).
+
+    python examples/quickstart.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from pogema_b200 import BatchedPogema, GridConfig, pogema_v0
+
+# 1. upstream-style single instance, Python lists in and out -------------------------------------------
+env = pogema_v0(GridConfig(size=8, density=0.3, num_agents=4, obs_radius=5, seed=0))
+obs, infos = env.reset()
+while True:
+    obs, reward, terminated, truncated, infos = env.step(env.sample_actions())
+    if all(terminated) or all(truncated):
+        break
+print("single instance metrics:", infos[0]["metrics"])
+
+# 2. closed loop on 4096 instances: a (toy) policy consumes the observation tensor on the GPU -----------
+cfg = GridConfig(size=32, density=0.3, num_agents=64, obs_radius=5, max_episode_steps=64)
+venv = BatchedPogema(cfg, num_envs=4096, auto_reset="reseed")        # a fresh random map for every episode
+policy = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 11 * 11, 5)).cuda().half()
+obs = venv.reset()                                                    # uint8 [4096, 64, 3, 11, 11]
+total = 0.0
+for t in range(128):
+    with torch.no_grad():
+        logits = policy(obs.view(-1, 3, 11, 11).half())
+    actions = logits.argmax(-1).view(4096, 64).to(torch.uint8)
+    obs, rewards, terminated, truncated = venv.step(actions)           # one kernel launch
+    total += float(rewards.sum())
+print("closed loop: %d agent-steps, total reward %.0f, seeds now %s..." % (128 * 4096 * 64, total, venv.current_seeds()[:3]))
+
+# 3. open loop: K steps per launch for actions known in advance ---------------------------------------------
+venv = BatchedPogema(cfg, num_envs=4096)                                # same-task auto reset
+venv.reset()
+ring = torch.empty((2,) + tuple(venv.engine.obs_shape()), dtype=torch.uint8, device="cuda")   # keep only 2 observations
+for launch in range(4):                                                 # 64 steps = one full episode
+    actions = torch.randint(0, 5, (16, 4096, 64), dtype=torch.uint8, device="cuda")
+    obs_k, rew_k, term_k, trunc_k = venv.rollout(actions, obs_out=ring)
+print("rollout:", tuple(rew_k.shape), "rewards in the last 16 steps", float(rew_k.sum()))
+print("metrics of the finished episodes:", {k: float(v.mean()) for k, v in venv.metrics().items()})
