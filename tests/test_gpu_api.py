@@ -306,3 +306,33 @@ def test_list_env_auto_reset_flag():
         if all(rte) or all(rtr):
             ro, _ = ref.reset()
         assert all(np.array_equal(x, y) for x, y in zip(o, ro)) and r == rr and te == rte and tr == rtr
+
+
+def test_c_abi_misuse_returns_status_codes():
+    """Call-order and argument errors come back as negative status codes with a message, never as a crash."""
+    import ctypes as C
+    from pogema_b200 import _native as nat
+    lib = nat.load()
+    cfg = nat.PgmConfig()
+    cfg.abi_version = nat.PGM_ABI_VERSION
+    cfg.device, cfg.num_envs, cfg.num_agents, cfg.height, cfg.width = 0, 2, 3, 8, 8
+    cfg.obs_radius, cfg.max_episode_steps = 2, 8
+    h = C.c_void_p()
+    assert lib.pgm_create(C.byref(cfg), C.byref(h)) == nat.PGM_OK
+    dummy = C.c_void_p(16)
+    assert lib.pgm_step(h, dummy, 1, None, dummy, dummy, dummy, None) == nat.PGM_ERR_STATE      # no tasks yet
+    assert b"before pgm_generate" in lib.pgm_last_error()
+    assert lib.pgm_reset(h, None, None) == nat.PGM_ERR_STATE
+    assert lib.pgm_step(h, dummy, 3, None, dummy, dummy, dummy, None) == nat.PGM_ERR_INVALID    # bad itemsize
+    seeds = (C.c_uint64 * 2)(1, 2)
+    assert lib.pgm_generate(h, 1, 2, seeds, C.c_double(0.3), None, 1, None, None) == nat.PGM_ERR_INVALID  # range
+    assert lib.pgm_generate(h, 0, 2, seeds, C.c_double(1.5), None, 1, None, None) == nat.PGM_ERR_INVALID  # density
+    assert lib.pgm_generate(h, 0, 2, seeds, C.c_double(0.3), None, 1, None, None) == nat.PGM_OK
+    assert lib.pgm_get_state(h, 99, dummy, 8, None) == nat.PGM_ERR_INVALID
+    small = (C.c_uint8 * 4)()
+    assert lib.pgm_get_state(h, nat.STATE_POSITIONS, small, 4, None) == nat.PGM_ERR_INVALID     # buffer too small
+    assert lib.pgm_destroy(h) == nat.PGM_OK
+    bad = nat.PgmConfig()
+    bad.abi_version = nat.PGM_ABI_VERSION
+    bad.device, bad.num_envs, bad.num_agents, bad.height, bad.width, bad.obs_radius, bad.max_episode_steps = 99, 1, 1, 8, 8, 2, 8
+    assert lib.pgm_create(C.byref(bad), C.byref(h)) == nat.PGM_ERR_INVALID                      # no such device
