@@ -9,8 +9,8 @@ BUILD := build
 LIB := pogema_b200/_lib/libpgm_b200.so
 INST := step_priority step_block_both step_soft observe reset
 CU := pgm_capi pgm_devgen $(foreach i,$(INST),pgm_inst_$(i)_g0 pgm_inst_$(i)_g1)
-OBJS := $(addprefix $(BUILD)/,$(addsuffix .o,$(CU))) $(BUILD)/pgm_gen.o
-HDRS := $(CSRC)/pgm_devgen.h $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h include/pgm_b200.h
+OBJS := $(addprefix $(BUILD)/,$(addsuffix .o,$(CU))) $(BUILD)/pgm_gen.o $(BUILD)/pgm_hostexpand.o
+HDRS := $(CSRC)/pgm_devgen.h $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h $(CSRC)/pgm_hostexpand.h include/pgm_b200.h
 
 all: $(LIB) oracle
 
@@ -19,6 +19,10 @@ $(BUILD)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(PTXAS_V) -c $< -o $@
 
 $(BUILD)/pgm_gen.o: $(CSRC)/pgm_gen.cpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(BUILD)/pgm_hostexpand.o: $(CSRC)/pgm_hostexpand.cpp $(HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) -O3 -std=c++17 -fPIC -Wall -c $< -o $@
 

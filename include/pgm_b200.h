@@ -207,6 +207,26 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
 /* upstream Pogema._obs with a HOST destination buffer (copies device->host, synchronises). */
 int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream);
 
+/*
+ * How pgm_step_host / pgm_observe_host bring PGM_OBS_U8 / PGM_OBS_F32 observations to the host.
+ *   mode 0 (plain):  the kernel writes the final tensor, the copy engine moves all of it (PCIe-bound:
+ *                    3*D*D bytes, or 4x that, per agent).
+ *   mode 1 (packed): the kernel writes the observation BIT STREAM (1 bit per element, every bit still
+ *                    computed on the GPU), the copy engine moves 1/8 (1/32) of the bytes in chunks into
+ *                    pinned staging owned by the engine, and `num_threads` host threads (0 = all cores,
+ *                    at most 32) widen bit k to element k of obs_host with non-temporal stores while
+ *                    later chunks are still on the bus.  obs_host receives exactly the bytes of mode 0.
+ *   mode -1 (auto, the default): packed when the tensor is >= 4 MB (env PGM_HOST_TRANSPORT=0/1 overrides).
+ */
+int pgm_set_host_transport(pgm_engine* e, int32_t mode, int32_t num_threads);
+/* out[0] 1 if the next host call uses the packed transport, [1] host threads of the pool (0 = not started),
+ * [2]/[3] host->device / device->host bytes moved by the last pgm_step_host, [4] host ISA of the widening
+ * loop (0 scalar, 1 AVX2, 2 AVX-512BW). */
+int pgm_host_transport_info(const pgm_engine* e, int64_t* out, int32_t n);
+/* The widening loop of the packed transport on its own (no CUDA call; used by the CPU tests): bit k of
+ * the little-endian word stream src_host -> element k of dst_host (elem_size 1: uint8 0/1, 4: float32). */
+int pgm_expand_bits_host(const uint32_t* src_host, int64_t nbits, void* dst_host, int32_t elem_size);
+
 /* State access (debugging, env.grid accessors, checkpoint/resume). */
 int pgm_get_state(pgm_engine* e, int32_t what, void* dst_host, int64_t dst_bytes, void* stream);
 void* pgm_state_ptr(pgm_engine* e, int32_t what); /* device pointer of the raw array, or NULL */

@@ -14,6 +14,7 @@
 #include "../../include/pgm_b200.h"
 #include "pgm_devgen.h"
 #include "pgm_gen.h"
+#include "pgm_hostexpand.h"
 #include "pgm_launch.cuh"
 
 using namespace pgm;
@@ -100,6 +101,16 @@ struct pgm_engine {
   int regen_slots = 0;
   int64_t launches = 0;
   bool use_pdl = true;
+  // packed host transport (pgm_step_host / pgm_observe_host): device bit stream -> pinned staging -> host threads
+  int host_transport = -1;      // -1 auto, 0 plain (DMA of the final tensor), 1 packed
+  int host_threads = 0;         // 0 = hardware concurrency (at most 32)
+  int64_t stream_unit_bytes = 0, stream_batch_bytes = 0, stream_bytes = 0;
+  uint8_t* d_stream = nullptr;  // device: [N][batches][stream_batch_bytes]
+  uint8_t* h_stream = nullptr;  // pinned host copy
+  std::vector<cudaEvent_t> stream_events;
+  pgm::ExpandPool* pool = nullptr;
+  bool ovr_stream = false;      // make_args: write the raw stream instead of cfg.obs_format
+  int64_t last_d2h_bytes = 0, last_h2d_bytes = 0;
 };
 
 namespace {
@@ -144,6 +155,7 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   long long g = (budget >= stage_bytes_for(A)) ? A : ((budget - 16) * 8) / per_agent_bits;
   if (g < 1) return false;
   g = std::min<long long>(g, A);
+  if (const char* v = getenv("PGM_OBS_BATCH")) g = std::max<long long>(1, std::min<long long>(g, atoi(v)));  // tuning knob
   const int stage_bytes = (int)stage_bytes_for(g);
   StepArgs& L = out->L;
   int off = 0;
@@ -323,6 +335,12 @@ StepArgs make_args(pgm_engine* e) {
   a.obs_slot_stride = 0;
   a.obs = nullptr;
   a.obs_inst_stride = e->obs_inst_stride;
+  a.stream_batch_bytes = 0;
+  if (e->ovr_stream) {
+    a.obs_format = 3;
+    a.obs_inst_stride = e->stream_unit_bytes;
+    a.stream_batch_bytes = (int)e->stream_batch_bytes;
+  }
   a.rewards = nullptr;
   a.terminated = nullptr;
   a.truncated = nullptr;
@@ -498,6 +516,99 @@ DevGenArgs devgen_args(pgm_engine* e, double density, bool has_map) {
 
 // auto_reset == 2: after a step, rebuild every instance whose episode ended from its next seed
 // (compact the flags -> device generator over the list -> masked observe pass)
+// ---- packed host transport ------------------------------------------------------------------------
+// The step kernel writes each instance's observation bit stream (obs_format 3), the copy engine moves it
+// to pinned staging in chunks, and host threads widen chunk c while chunk c+1 is still on the bus.
+constexpr int kStreamChunks = 8;
+
+bool use_packed(const pgm_engine* e) {
+  if (e->cfg.obs_format == PGM_OBS_BITS) return false;
+  if (e->host_transport >= 0) return e->host_transport == 1;
+  if (const char* v = getenv("PGM_HOST_TRANSPORT")) return v[0] == '1' || v[0] == 'p';
+  return e->obs_bytes >= (4 << 20);  // auto: below a few MB the DMA of the final tensor is latency-, not PCIe-bound
+}
+
+int ensure_stream(pgm_engine* e) {
+  if (!e->d_stream) {
+    const int64_t A = e->cfg.num_agents, g = e->batch_agents;
+    const int64_t batches = (A + g - 1) / g;
+    e->stream_batch_bytes = (int64_t)round_up((int)((g * e->bits_per_agent + 31) / 32), 4) * 4;
+    e->stream_unit_bytes = batches * e->stream_batch_bytes;
+    e->stream_bytes = e->stream_unit_bytes * e->cfg.num_envs;
+    CUDA_TRY(cudaMalloc((void**)&e->d_stream, (size_t)e->stream_bytes + 64));
+    CUDA_TRY(cudaHostAlloc((void**)&e->h_stream, (size_t)e->stream_bytes + 64, cudaHostAllocDefault));
+    memset(e->h_stream, 0, (size_t)e->stream_bytes + 64);
+    e->stream_events.resize(kStreamChunks);
+    for (auto& ev : e->stream_events) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  if (!e->pool) {
+    int t = e->host_threads;
+    if (t <= 0) {
+      if (const char* v = getenv("PGM_HOST_THREADS")) t = atoi(v);
+    }
+    if (t <= 0) t = std::min(32, std::max(1, (int)std::thread::hardware_concurrency()));
+    e->pool = new pgm::ExpandPool(t);
+  }
+  return PGM_OK;
+}
+
+void begin_expand(pgm_engine* e, void* obs_host) {
+  pgm::ExpandJob j;
+  const int64_t A = e->cfg.num_agents, g = e->batch_agents;
+  j.src = e->h_stream;
+  j.dst = (uint8_t*)obs_host;
+  j.units = e->cfg.num_envs;
+  j.src_unit_stride = e->stream_unit_bytes;
+  j.dst_unit_stride = e->obs_inst_stride;
+  j.batches = (A + g - 1) / g;
+  j.src_batch_stride = e->stream_batch_bytes;
+  j.batch_elems = g * e->bits_per_agent;
+  j.unit_elems = A * e->bits_per_agent;
+  j.elem_size = e->cfg.obs_format == PGM_OBS_F32 ? 4 : 1;
+  e->pool->begin(j);
+}
+
+void abort_expand(pgm_engine* e) {
+  // a failed launch: let the workers run over whatever the staging buffer holds (the caller ignores the
+  // output of a failed call) so that the pool is idle again
+  e->pool->publish(e->cfg.num_envs);
+  e->pool->finish();
+}
+
+int enqueue_stream_copies(pgm_engine* e, cudaStream_t s) {
+  const int64_t N = e->cfg.num_envs;
+  for (int c = 0; c < kStreamChunks; ++c) {
+    const int64_t u0 = N * c / kStreamChunks, u1 = N * (c + 1) / kStreamChunks;
+    if (u1 > u0) {
+      cudaError_t err = cudaMemcpyAsync(e->h_stream + u0 * e->stream_unit_bytes, e->d_stream + u0 * e->stream_unit_bytes,
+                                        (size_t)((u1 - u0) * e->stream_unit_bytes), cudaMemcpyDeviceToHost, s);
+      if (err == cudaSuccess) err = cudaEventRecord(e->stream_events[c], s);
+      if (err != cudaSuccess) {
+        abort_expand(e);
+        return fail(PGM_ERR_CUDA, "stream copy failed: %s", cudaGetErrorString(err));
+      }
+    }
+  }
+  return PGM_OK;
+}
+
+int drain_expand(pgm_engine* e) {
+  const int64_t N = e->cfg.num_envs;
+  for (int c = 0; c < kStreamChunks; ++c) {
+    const int64_t u0 = N * c / kStreamChunks, u1 = N * (c + 1) / kStreamChunks;
+    if (u1 > u0) {
+      cudaError_t err = cudaEventSynchronize(e->stream_events[c]);
+      if (err != cudaSuccess) {
+        abort_expand(e);
+        return fail(PGM_ERR_CUDA, "stream copy failed: %s", cudaGetErrorString(err));
+      }
+      e->pool->publish(u1);
+    }
+  }
+  e->pool->finish();
+  return PGM_OK;
+}
+
 int enqueue_rebuilds(pgm_engine* e, void* obs_dev, cudaStream_t s) {
   if (e->gen_density < 0.0 || e->gen_explicit)
     return fail(PGM_ERR_STATE, "auto_reset=2 needs tasks built by pgm_generate / pgm_generate_device");
@@ -630,6 +741,10 @@ int pgm_destroy(pgm_engine* e) {
                   e->d_rew_h, e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  delete e->pool;
+  if (e->d_stream) cudaFree(e->d_stream);
+  if (e->h_stream) cudaFreeHost(e->h_stream);
+  for (cudaEvent_t ev : e->stream_events) cudaEventDestroy(ev);
   delete e;
   return PGM_OK;
 }
@@ -865,6 +980,39 @@ int pgm_step_many(pgm_engine* e, int32_t num_steps, const void* actions_dev, int
   return launch(e, a, OP_STEP, (cudaStream_t)stream);
 }
 
+int pgm_set_host_transport(pgm_engine* e, int32_t mode, int32_t num_threads) {
+  if (!e) return fail(PGM_ERR_INVALID, "null engine");
+  if (mode < -1 || mode > 1) return fail(PGM_ERR_INVALID, "host transport mode must be -1 (auto), 0 (plain) or 1 (packed)");
+  if (num_threads < 0) return fail(PGM_ERR_INVALID, "num_threads must be >= 0");
+  if (mode == 1 && e->cfg.obs_format == PGM_OBS_BITS)
+    return fail(PGM_ERR_INVALID, "obs_format=bits is already packed: nothing to expand on the host");
+  e->host_transport = mode;
+  if (num_threads != e->host_threads) {
+    delete e->pool;
+    e->pool = nullptr;
+    e->host_threads = num_threads;
+  }
+  return PGM_OK;
+}
+
+int pgm_host_transport_info(const pgm_engine* e, int64_t* out, int32_t n) {
+  if (!e || !out) return fail(PGM_ERR_INVALID, "null argument");
+  const int64_t v[5] = {use_packed(e) ? 1 : 0, e->pool ? e->pool->threads() : 0, e->last_h2d_bytes, e->last_d2h_bytes,
+                        pgm::expand_isa()[0] == 'a' ? (pgm::expand_isa()[3] == '5' ? 2 : 1) : 0};
+  for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
+  return PGM_OK;
+}
+
+int pgm_expand_bits_host(const uint32_t* src_host, int64_t nbits, void* dst_host, int32_t elem_size) {
+  if (!src_host || !dst_host || nbits < 0) return fail(PGM_ERR_INVALID, "bad argument");
+  if (elem_size != 1 && elem_size != 4) return fail(PGM_ERR_INVALID, "elem_size must be 1 (uint8) or 4 (float32)");
+  // the vector paths may read up to 16 bytes past the last stream word: go through a padded copy
+  std::vector<uint32_t> tmp((size_t)((nbits + 31) / 32) + 8, 0u);
+  memcpy(tmp.data(), src_host, (size_t)((nbits + 31) / 32) * 4);
+  pgm::expand_bits(tmp.data(), (size_t)nbits, dst_host, elem_size);
+  return PGM_OK;
+}
+
 int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsize, void* obs_host,
                   float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream) {
   if (!e || !actions_host || !rewards_host || !terminated_host || !truncated_host)
@@ -876,14 +1024,29 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
   if (rc != PGM_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t NA = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+  const bool packed = obs_host && use_packed(e);
+  if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
+  if (packed) begin_expand(e, obs_host);  // wake the host threads under the upload + kernel
   CUDA_TRY(cudaMemcpyAsync(e->d_act_h, actions_host, NA * action_itemsize, cudaMemcpyHostToDevice, s));
-  rc = pgm_step(e, e->d_act_h, action_itemsize, obs_host ? e->d_obs_h : nullptr, e->d_rew_h, e->d_term_h,
-                e->d_trunc_h, stream);
-  if (rc != PGM_OK) return rc;
-  if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+  e->ovr_stream = packed;
+  rc = pgm_step(e, e->d_act_h, action_itemsize, obs_host ? (packed ? e->d_stream : e->d_obs_h) : nullptr, e->d_rew_h,
+                e->d_term_h, e->d_trunc_h, stream);
+  e->ovr_stream = false;
+  if (rc != PGM_OK) {
+    if (packed) abort_expand(e);
+    return rc;
+  }
+  e->last_h2d_bytes = (int64_t)(NA * action_itemsize);
+  e->last_d2h_bytes = (int64_t)(NA * 6) + (obs_host ? (packed ? e->stream_bytes : e->obs_bytes) : 0);
+  if (packed) {
+    if ((rc = enqueue_stream_copies(e, s)) != PGM_OK) return rc;
+  } else if (obs_host) {
+    CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(cudaMemcpyAsync(rewards_host, e->d_rew_h, NA * 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(terminated_host, e->d_term_h, NA, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(truncated_host, e->d_trunc_h, NA, cudaMemcpyDeviceToHost, s));
+  if (packed && (rc = drain_expand(e)) != PGM_OK) return rc;
   CUDA_TRY(cudaStreamSynchronize(s));
   return PGM_OK;
 }
@@ -893,10 +1056,23 @@ int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream) {
   DeviceGuard guard(e->cfg.device);
   int rc = ensure_host_scratch(e, 1);
   if (rc != PGM_OK) return rc;
-  rc = pgm_observe(e, e->d_obs_h, stream);
-  if (rc != PGM_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+  const bool packed = use_packed(e);
+  if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
+  if (packed) begin_expand(e, obs_host);
+  e->ovr_stream = packed;
+  rc = pgm_observe(e, packed ? e->d_stream : e->d_obs_h, stream);
+  e->ovr_stream = false;
+  if (rc != PGM_OK) {
+    if (packed) abort_expand(e);
+    return rc;
+  }
+  if (packed) {
+    if ((rc = enqueue_stream_copies(e, s)) != PGM_OK) return rc;
+    if ((rc = drain_expand(e)) != PGM_OK) return rc;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   return PGM_OK;
 }

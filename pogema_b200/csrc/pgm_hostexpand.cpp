@@ -1,0 +1,237 @@
+// pgm_hostexpand.cpp - bit stream -> uint8 / float32 expansion on the host (see pgm_hostexpand.h).
+//
+// This is the receiving end of a transport encoding, not a compute path: every bit was produced by the
+// step kernel on the GPU (pgm_kernels.cuh, obs_format 3); the host only widens bit k to element k.
+#include "pgm_hostexpand.h"
+
+#include <immintrin.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace pgm {
+namespace {
+
+inline uint64_t get64(const uint8_t* src, size_t bitpos) {
+  unsigned __int128 v;
+  memcpy(&v, src + (bitpos >> 3), 16);
+  return (uint64_t)(v >> (bitpos & 7));
+}
+inline uint64_t lowmask(size_t n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
+
+// ----------------------------------------------------------------------------- scalar
+struct Lut {
+  uint64_t t[256];
+  Lut() {
+    for (int b = 0; b < 256; ++b) {
+      uint64_t v = 0;
+      for (int i = 0; i < 8; ++i) v |= (uint64_t)((b >> i) & 1) << (8 * i);
+      t[b] = v;
+    }
+  }
+};
+const Lut g_lut;
+
+void expand_u8_scalar(const uint8_t* src, size_t nbits, uint8_t* dst) {
+  size_t pos = 0;
+  for (; pos + 8 <= nbits; pos += 8) memcpy(dst + pos, &g_lut.t[src[pos >> 3]], 8);
+  for (; pos < nbits; ++pos) dst[pos] = (src[pos >> 3] >> (pos & 7)) & 1;
+}
+void expand_f32_scalar(const uint8_t* src, size_t nbits, float* dst) {
+  for (size_t pos = 0; pos < nbits; ++pos) dst[pos] = ((src[pos >> 3] >> (pos & 7)) & 1) ? 1.0f : 0.0f;
+}
+
+// ----------------------------------------------------------------------------- AVX-512
+__attribute__((target("avx512f,avx512bw"))) void expand_u8_avx512(const uint8_t* src, size_t nbits, uint8_t* dst) {
+  const __m512i one = _mm512_set1_epi8(1);
+  size_t pos = std::min(nbits, (size_t)((64 - ((uintptr_t)dst & 63)) & 63));
+  if (pos) {
+    const __mmask64 k = lowmask(pos);
+    _mm512_mask_storeu_epi8(dst, k, _mm512_maskz_mov_epi8(get64(src, 0) & k, one));
+  }
+  for (; pos + 64 <= nbits; pos += 64)
+    _mm512_stream_si512((__m512i*)(dst + pos), _mm512_maskz_mov_epi8(get64(src, pos), one));
+  if (pos < nbits) {
+    const __mmask64 k = lowmask(nbits - pos);
+    _mm512_mask_storeu_epi8(dst + pos, k, _mm512_maskz_mov_epi8(get64(src, pos) & k, one));
+  }
+}
+__attribute__((target("avx512f,avx512bw"))) void expand_f32_avx512(const uint8_t* src, size_t nbits, float* dst) {
+  const __m512 one = _mm512_set1_ps(1.0f);
+  size_t pos = std::min(nbits, (size_t)(((64 - ((uintptr_t)dst & 63)) & 63) >> 2));
+  if (pos) {
+    const __mmask16 k = (__mmask16)lowmask(pos);
+    _mm512_mask_storeu_ps(dst, k, _mm512_maskz_mov_ps((__mmask16)get64(src, 0) & k, one));
+  }
+  for (; pos + 64 <= nbits; pos += 64) {
+    const uint64_t m = get64(src, pos);
+    _mm512_stream_ps(dst + pos, _mm512_maskz_mov_ps((__mmask16)m, one));
+    _mm512_stream_ps(dst + pos + 16, _mm512_maskz_mov_ps((__mmask16)(m >> 16), one));
+    _mm512_stream_ps(dst + pos + 32, _mm512_maskz_mov_ps((__mmask16)(m >> 32), one));
+    _mm512_stream_ps(dst + pos + 48, _mm512_maskz_mov_ps((__mmask16)(m >> 48), one));
+  }
+  for (; pos < nbits; pos += 16) {
+    const __mmask16 k = (__mmask16)lowmask(std::min<size_t>(16, nbits - pos));
+    _mm512_mask_storeu_ps(dst + pos, k, _mm512_maskz_mov_ps((__mmask16)get64(src, pos) & k, one));
+  }
+}
+
+// ----------------------------------------------------------------------------- AVX2
+__attribute__((target("avx2"))) void expand_u8_avx2(const uint8_t* src, size_t nbits, uint8_t* dst) {
+  size_t pos = std::min(nbits, (size_t)((32 - ((uintptr_t)dst & 31)) & 31));
+  for (size_t i = 0; i < pos; ++i) dst[i] = (src[i >> 3] >> (i & 7)) & 1;
+  const __m256i shuf = _mm256_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3,
+                                        3, 3, 3, 3, 3);
+  const __m256i bit = _mm256_set1_epi64x((long long)0x8040201008040201ull);
+  const __m256i one = _mm256_set1_epi8(1);
+  for (; pos + 32 <= nbits; pos += 32) {
+    __m256i v = _mm256_shuffle_epi8(_mm256_set1_epi32((int)(uint32_t)get64(src, pos)), shuf);
+    v = _mm256_and_si256(_mm256_cmpeq_epi8(_mm256_and_si256(v, bit), bit), one);
+    _mm256_stream_si256((__m256i*)(dst + pos), v);
+  }
+  for (; pos < nbits; ++pos) dst[pos] = (src[pos >> 3] >> (pos & 7)) & 1;
+}
+__attribute__((target("avx2"))) void expand_f32_avx2(const uint8_t* src, size_t nbits, float* dst) {
+  size_t pos = std::min(nbits, (size_t)(((32 - ((uintptr_t)dst & 31)) & 31) >> 2));
+  for (size_t i = 0; i < pos; ++i) dst[i] = ((src[i >> 3] >> (i & 7)) & 1) ? 1.0f : 0.0f;
+  const __m256i bit = _mm256_setr_epi32(1, 2, 4, 8, 16, 32, 64, 128);
+  const __m256 one = _mm256_set1_ps(1.0f);
+  for (; pos + 8 <= nbits; pos += 8) {
+    const __m256i v = _mm256_set1_epi32((int)(get64(src, pos) & 0xFF));
+    const __m256i hit = _mm256_cmpeq_epi32(_mm256_and_si256(v, bit), bit);
+    _mm256_stream_ps(dst + pos, _mm256_and_ps(_mm256_castsi256_ps(hit), one));
+  }
+  for (; pos < nbits; ++pos) dst[pos] = ((src[pos >> 3] >> (pos & 7)) & 1) ? 1.0f : 0.0f;
+}
+
+int detect_isa() {
+  if (const char* v = getenv("PGM_HOST_ISA")) {  // testing knob: scalar | avx2 | avx512bw
+    if (!strcmp(v, "scalar")) return 0;
+    if (!strcmp(v, "avx2") && __builtin_cpu_supports("avx2")) return 1;
+  }
+  if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) return 2;
+  if (__builtin_cpu_supports("avx2")) return 1;
+  return 0;
+}
+int isa() {
+  static const int v = detect_isa();
+  return v;
+}
+
+}  // namespace
+
+const char* expand_isa() { return isa() == 2 ? "avx512bw" : (isa() == 1 ? "avx2" : "scalar"); }
+
+void expand_bits(const uint32_t* src32, size_t nbits, void* dst, int elem_size) {
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(src32);
+  const int k = isa();
+  if (elem_size == 1) {
+    if (k == 2) expand_u8_avx512(src, nbits, (uint8_t*)dst);
+    else if (k == 1) expand_u8_avx2(src, nbits, (uint8_t*)dst);
+    else expand_u8_scalar(src, nbits, (uint8_t*)dst);
+  } else {
+    if (((uintptr_t)dst & 3) != 0) expand_f32_scalar(src, nbits, (float*)dst);
+    else if (k == 2) expand_f32_avx512(src, nbits, (float*)dst);
+    else if (k == 1) expand_f32_avx2(src, nbits, (float*)dst);
+    else expand_f32_scalar(src, nbits, (float*)dst);
+  }
+}
+
+// ----------------------------------------------------------------------------- thread pool
+struct ExpandPool::Impl {
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_start, cv_done;
+  uint64_t generation = 0;
+  bool stop = false;
+  int running = 0;
+  ExpandJob job;
+  int64_t grain = 1;
+  alignas(64) std::atomic<int64_t> next{0};
+  alignas(64) std::atomic<int64_t> ready{0};
+
+  void run_job() {
+    const ExpandJob& j = job;
+    for (;;) {
+      const int64_t u0 = next.fetch_add(grain, std::memory_order_relaxed);
+      if (u0 >= j.units) break;
+      const int64_t u1 = std::min(j.units, u0 + grain);
+      int spins = 0;
+      while (ready.load(std::memory_order_acquire) < u1) {
+        if (++spins < 2000) _mm_pause();
+        else std::this_thread::yield();
+      }
+      for (int64_t u = u0; u < u1; ++u) {
+        const uint8_t* s = j.src + u * j.src_unit_stride;
+        uint8_t* d = j.dst + u * j.dst_unit_stride;
+        int64_t left = j.unit_elems;
+        for (int64_t b = 0; b < j.batches && left > 0; ++b) {
+          const int64_t n = std::min(left, j.batch_elems);
+          expand_bits(reinterpret_cast<const uint32_t*>(s + b * j.src_batch_stride), (size_t)n,
+                      d + b * j.batch_elems * j.elem_size, j.elem_size);
+          left -= n;
+        }
+      }
+    }
+    _mm_sfence();  // non-temporal stores are globally visible before the job is reported done
+  }
+
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_start.wait(lk, [&] { return stop || generation != seen; });
+        if (stop) return;
+        seen = generation;
+      }
+      run_job();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--running == 0) cv_done.notify_all();
+      }
+    }
+  }
+};
+
+ExpandPool::ExpandPool(int threads) : impl_(new Impl()), nthreads_(std::max(1, threads)) {
+  for (int i = 0; i < nthreads_; ++i) impl_->workers.emplace_back([this] { impl_->worker(); });
+}
+
+ExpandPool::~ExpandPool() {
+  {
+    std::lock_guard<std::mutex> lk(impl_->mu);
+    impl_->stop = true;
+  }
+  impl_->cv_start.notify_all();
+  for (auto& t : impl_->workers) t.join();
+  delete impl_;
+}
+
+void ExpandPool::begin(const ExpandJob& job) {
+  std::lock_guard<std::mutex> lk(impl_->mu);
+  impl_->job = job;
+  // ~64 KB of output per claim: coarse enough to amortise the atomic, fine enough to balance the tail
+  const int64_t unit_bytes = std::max<int64_t>(1, job.unit_elems * job.elem_size);
+  impl_->grain = std::max<int64_t>(1, std::min<int64_t>((64 * 1024) / unit_bytes,
+                                                          (job.units + 4 * nthreads_ - 1) / (4 * nthreads_)));
+  impl_->next.store(0, std::memory_order_relaxed);
+  impl_->ready.store(0, std::memory_order_relaxed);
+  impl_->running = nthreads_;
+  impl_->generation++;
+  impl_->cv_start.notify_all();
+}
+
+void ExpandPool::publish(int64_t ready_units) { impl_->ready.store(ready_units, std::memory_order_release); }
+
+void ExpandPool::finish() {
+  std::unique_lock<std::mutex> lk(impl_->mu);
+  impl_->cv_done.wait(lk, [&] { return impl_->running == 0; });
+}
+
+}  // namespace pgm

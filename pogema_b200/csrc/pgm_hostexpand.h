@@ -1,0 +1,47 @@
+// pgm_hostexpand.h - host half of the packed observation transport of pgm_step_host / pgm_observe_host.
+//
+// The device writes an instance's observations as a contiguous BIT stream (1 bit per element of upstream
+// envs.py :: _get_agents_obs, 8x / 32x smaller than the uint8 / float32 tensor), the copy engine moves that
+// stream over PCIe, and a pool of host threads turns bits into the caller's uint8 / float32 buffer with
+// non-temporal 64-byte stores while later chunks are still in flight.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace pgm {
+
+// One contiguous run of the stream: bit k of `src` (little endian 32-bit words) -> element k of `dst`.
+// elem_size 1: uint8 0/1; 4: float32 0.0/1.0.  `src` may be over-read by up to 16 bytes.
+void expand_bits(const uint32_t* src, size_t nbits, void* dst, int elem_size);
+const char* expand_isa();  // "avx512bw" | "avx2" | "scalar"
+
+// Geometry of the packed stream of a whole observation tensor.
+struct ExpandJob {
+  const uint8_t* src = nullptr;  // pinned staging copy of the device stream
+  uint8_t* dst = nullptr;        // caller's observation buffer
+  int64_t units = 0;             // instances
+  int64_t src_unit_stride = 0;   // bytes between instances in the stream
+  int64_t dst_unit_stride = 0;   // bytes between instances in dst
+  int64_t batches = 1;           // observation batches per instance (each starts on a 16-byte boundary)
+  int64_t src_batch_stride = 0;  // bytes
+  int64_t batch_elems = 0;       // elements (= bits) per full batch
+  int64_t unit_elems = 0;        // elements per instance
+  int elem_size = 1;
+};
+
+class ExpandPool {
+ public:
+  explicit ExpandPool(int threads);
+  ~ExpandPool();
+  int threads() const { return nthreads_; }
+  // begin(): wake the workers; they expand units as publish() makes them available.
+  void begin(const ExpandJob& job);
+  void publish(int64_t ready_units);  // units [0, ready_units) of src are complete
+  void finish();                      // returns when every unit has been expanded (sfence'd)
+ private:
+  struct Impl;
+  Impl* impl_;
+  int nthreads_;
+};
+
+}  // namespace pgm

@@ -46,7 +46,9 @@ struct StepArgs {
   int obst_stride;      // uint32 words per instance (multiple of 4, >= PH*WPR + 1)
   int bits_per_agent;   // 3*D*D
   int stage_bpa;        // stage bits per agent: bits_per_agent (U8) or rounded up to 32 (BITS)
-  int obs_format;       // 0 u8, 1 bits, 2 float32
+  int obs_format;       // 0 u8, 1 bits, 2 float32, 3 raw stream (packed host transport: the stage bit stream of
+                        // every observation batch as it is, batches stream_batch_bytes apart)
+  int stream_batch_bytes;
   int max_steps, auto_reset;
   int on_target;        // 0 finish, 1 nothing, 2 restart
   int batch_agents;     // agents per observation batch (stage capacity)
@@ -381,7 +383,13 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* 
     team_sync<TEAM>(bar_id);
     PGM_STAMP(7);
     // ---- write out
-    if (p.obs_format == 1) {
+    if (p.obs_format == 3) {
+      // packed host transport (pgm_step_host): the bit stream itself, 16-byte stores; the host widens it
+      uint4* out = reinterpret_cast<uint4*>(obs + (long long)n * p.obs_inst_stride +
+                                            (long long)(g0 / p.batch_agents) * p.stream_batch_bytes);
+      const int nv = ((nbits + 31) / 32 + 3) >> 2;
+      for (int w = tid; w < nv; w += TEAM) __stcs(out + w, stage4[w]);
+    } else if (p.obs_format == 1) {
       const int wpa = sbpa >> 5;
       uint32_t* out = reinterpret_cast<uint32_t*>(obs + (long long)n * p.obs_inst_stride) + (long long)g0 * wpa;
       for (int w = tid; w < gcount * wpa; w += TEAM) __stcs(out + w, stage[w]);

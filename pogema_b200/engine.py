@@ -142,6 +142,19 @@ class Engine:
         nat.check(self.lib.pgm_step_host(self.handle, _ptr(actions), actions.itemsize, _ptr(obs), _ptr(rewards),
                                          _ptr(terminated), _ptr(truncated), C.c_void_p(stream)))
 
+    def set_host_transport(self, mode="auto", num_threads: int = 0):
+        """How step_host / observe_host bring observations to the host (pgm_set_host_transport):
+        'plain' = DMA of the final tensor, 'packed' = DMA of the GPU-written bit stream + host threads that
+        widen it into the caller's buffer, 'auto' = packed for tensors of 4 MB and more."""
+        m = {"auto": -1, "plain": 0, "packed": 1}[mode]
+        nat.check(self.lib.pgm_set_host_transport(self.handle, m, int(num_threads)))
+
+    def host_transport_info(self) -> dict:
+        out = (C.c_int64 * 5)()
+        nat.check(self.lib.pgm_host_transport_info(self.handle, out, 5))
+        return {"packed": bool(out[0]), "threads": int(out[1]), "h2d_bytes": int(out[2]), "d2h_bytes": int(out[3]),
+                "isa": ["scalar", "avx2", "avx512bw"][int(out[4])]}
+
     def observe_host(self, stream: int = 0) -> np.ndarray:
         """Observation of the current state as a host array (pgm_observe_host)."""
         out = np.empty(self.obs_shape(), dtype=self.obs_dtype())
