@@ -221,7 +221,9 @@ int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream);
 int pgm_set_host_transport(pgm_engine* e, int32_t mode, int32_t num_threads);
 /* out[0] 1 if the next host call uses the packed transport, [1] host threads of the pool (0 = not started),
  * [2]/[3] host->device / device->host bytes moved by the last pgm_step_host, [4] host ISA of the widening
- * loop (0 scalar, 1 AVX2, 2 AVX-512BW). */
+ * loop (0 scalar, 1 AVX2, 2 AVX-512BW), [5..9] microseconds from the entry of the last packed
+ * pgm_step_host to: all work enqueued, first chunk on the host, last chunk on the host, widening done,
+ * stream idle (= return). */
 int pgm_host_transport_info(const pgm_engine* e, int64_t* out, int32_t n);
 /* The widening loop of the packed transport on its own (no CUDA call; used by the CPU tests): bit k of
  * the little-endian word stream src_host -> element k of dst_host (elem_size 1: uint8 0/1, 4: float32). */

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -66,6 +67,7 @@ struct pgm_engine {
   int sm_count = 148;
   // plan
   int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1, occ_mode = 0, obst_global = 0;
+  int batch_single = 1;  // observation batch of single-step launches (pgm_step), <= batch_agents
   StepArgs layout{};  // offsets only
   // device state
   uint32_t* d_obst = nullptr;
@@ -107,10 +109,15 @@ struct pgm_engine {
   int64_t stream_unit_bytes = 0, stream_batch_bytes = 0, stream_bytes = 0;
   uint8_t* d_stream = nullptr;  // device: [N][batches][stream_batch_bytes]
   uint8_t* h_stream = nullptr;  // pinned host copy
-  std::vector<cudaEvent_t> stream_events;
+  uint32_t* d_flags = nullptr;  // device: [chunks] the step's epoch byte, copied to h_flags[c] right after chunk c
+  uint32_t* h_flags = nullptr;  // pinned: polled by the host threads
+  uint32_t epoch = 0;
   pgm::ExpandPool* pool = nullptr;
   bool ovr_stream = false;      // make_args: write the raw stream instead of cfg.obs_format
   int64_t last_d2h_bytes = 0, last_h2d_bytes = 0;
+  int64_t last_us[5] = {0, 0, 0, 0, 0};  // packed pgm_step_host: enqueue done, first chunk landed, last chunk landed, widening done, stream idle
+  std::chrono::steady_clock::time_point t_call;
+  int stream_chunks = 8;
 };
 
 namespace {
@@ -237,6 +244,11 @@ int compute_plan(pgm_engine* e) {
   if (team != 32 && team != 64 && team != 128 && team != 256 && team != 512 && team != 1024)
     return fail(PGM_ERR_INVALID, "team_threads must be 0 or a power of two in [32,1024], got %d", team);
   e->team = team;
+  // Single-step launches (pgm_step, closed loop): all teams reach the store phase together, so splitting the
+  // observation phase in two lets the first half's stores drain under the second half's bit assembly
+  // (measured: configs[1] 22.6 -> 21.7 us, configs[2] 26.6 -> 24.7 us per step; 512-thread teams lose).
+  e->batch_single = e->batch_agents;
+  if (!getenv("PGM_OBS_BATCH") && e->batch_agents == A && team <= 128 && A >= 2 * team) e->batch_single = std::max(team, A / 2);
   // teams per CTA: balance the busiest SM (CTAs are dealt round-robin, every SM should host the same
   // number of instances), prefer CTAs of 192..512 threads (measured: smaller CTAs cost ~15 %)
   int max_tpc = std::min(1024 / team, std::max(1, smem_max / L.team_smem));
@@ -519,7 +531,10 @@ DevGenArgs devgen_args(pgm_engine* e, double density, bool has_map) {
 // ---- packed host transport ------------------------------------------------------------------------
 // The step kernel writes each instance's observation bit stream (obs_format 3), the copy engine moves it
 // to pinned staging in chunks, and host threads widen chunk c while chunk c+1 is still on the bus.
-constexpr int kStreamChunks = 8;
+constexpr int kMaxStreamChunks = 64;
+inline int64_t us_since(const pgm_engine* e) {
+  return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - e->t_call).count();
+}
 
 bool use_packed(const pgm_engine* e) {
   if (e->cfg.obs_format == PGM_OBS_BITS) return false;
@@ -538,15 +553,18 @@ int ensure_stream(pgm_engine* e) {
     CUDA_TRY(cudaMalloc((void**)&e->d_stream, (size_t)e->stream_bytes + 64));
     CUDA_TRY(cudaHostAlloc((void**)&e->h_stream, (size_t)e->stream_bytes + 64, cudaHostAllocDefault));
     memset(e->h_stream, 0, (size_t)e->stream_bytes + 64);
-    e->stream_events.resize(kStreamChunks);
-    for (auto& ev : e->stream_events) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char* v = getenv("PGM_STREAM_CHUNKS")) e->stream_chunks = std::max(1, std::min(kMaxStreamChunks, atoi(v)));
+    e->stream_chunks = (int)std::min<int64_t>(e->stream_chunks, e->cfg.num_envs);
+    CUDA_TRY(cudaMalloc((void**)&e->d_flags, (size_t)kMaxStreamChunks * 4));
+    CUDA_TRY(cudaHostAlloc((void**)&e->h_flags, (size_t)kMaxStreamChunks * 4, cudaHostAllocDefault));
+    memset(e->h_flags, 0, (size_t)kMaxStreamChunks * 4);
   }
   if (!e->pool) {
     int t = e->host_threads;
     if (t <= 0) {
       if (const char* v = getenv("PGM_HOST_THREADS")) t = atoi(v);
     }
-    if (t <= 0) t = std::min(32, std::max(1, (int)std::thread::hardware_concurrency()));
+    if (t <= 0) t = std::min(32, std::max(1, (int)std::thread::hardware_concurrency()));  // the caller is one of them
     e->pool = new pgm::ExpandPool(t);
   }
   return PGM_OK;
@@ -565,47 +583,47 @@ void begin_expand(pgm_engine* e, void* obs_host) {
   j.batch_elems = g * e->bits_per_agent;
   j.unit_elems = A * e->bits_per_agent;
   j.elem_size = e->cfg.obs_format == PGM_OBS_F32 ? 4 : 1;
+  e->epoch = e->epoch % 255u + 1u;  // 1..255, never the value the flags hold from the previous call
+  j.flags = e->h_flags;
+  j.flag_value = e->epoch * 0x01010101u;
+  j.chunks = e->stream_chunks;
   e->pool->begin(j);
 }
 
 void abort_expand(pgm_engine* e) {
-  // a failed launch: let the workers run over whatever the staging buffer holds (the caller ignores the
-  // output of a failed call) so that the pool is idle again
-  e->pool->publish(e->cfg.num_envs);
+  // a failed call: the threads stop waiting for flags and run over whatever the staging buffer holds
+  // (the caller ignores the output of a failed call), so that the pool is idle again
+  e->pool->abort();
+  e->pool->work();
   e->pool->finish();
 }
 
+// Chunked copy of the device stream; the flag copy behind chunk c is stream-ordered after it, so a host
+// thread that reads flags[c] == epoch also sees the chunk.
 int enqueue_stream_copies(pgm_engine* e, cudaStream_t s) {
   const int64_t N = e->cfg.num_envs;
-  for (int c = 0; c < kStreamChunks; ++c) {
-    const int64_t u0 = N * c / kStreamChunks, u1 = N * (c + 1) / kStreamChunks;
-    if (u1 > u0) {
-      cudaError_t err = cudaMemcpyAsync(e->h_stream + u0 * e->stream_unit_bytes, e->d_stream + u0 * e->stream_unit_bytes,
-                                        (size_t)((u1 - u0) * e->stream_unit_bytes), cudaMemcpyDeviceToHost, s);
-      if (err == cudaSuccess) err = cudaEventRecord(e->stream_events[c], s);
-      if (err != cudaSuccess) {
-        abort_expand(e);
-        return fail(PGM_ERR_CUDA, "stream copy failed: %s", cudaGetErrorString(err));
-      }
-    }
+  const int C = e->stream_chunks;
+  cudaError_t err = cudaMemsetAsync(e->d_flags, (int)e->epoch, (size_t)C * 4, s);
+  for (int c = 0; c < C && err == cudaSuccess; ++c) {
+    const int64_t u0 = N * c / C, u1 = N * (c + 1) / C;
+    err = cudaMemcpyAsync(e->h_stream + u0 * e->stream_unit_bytes, e->d_stream + u0 * e->stream_unit_bytes,
+                          (size_t)((u1 - u0) * e->stream_unit_bytes), cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(e->h_flags + c, e->d_flags + c, 4, cudaMemcpyDeviceToHost, s);
+  }
+  if (err != cudaSuccess) {
+    abort_expand(e);
+    return fail(PGM_ERR_CUDA, "stream copy failed: %s", cudaGetErrorString(err));
   }
   return PGM_OK;
 }
 
 int drain_expand(pgm_engine* e) {
-  const int64_t N = e->cfg.num_envs;
-  for (int c = 0; c < kStreamChunks; ++c) {
-    const int64_t u0 = N * c / kStreamChunks, u1 = N * (c + 1) / kStreamChunks;
-    if (u1 > u0) {
-      cudaError_t err = cudaEventSynchronize(e->stream_events[c]);
-      if (err != cudaSuccess) {
-        abort_expand(e);
-        return fail(PGM_ERR_CUDA, "stream copy failed: %s", cudaGetErrorString(err));
-      }
-      e->pool->publish(u1);
-    }
-  }
+  e->last_us[0] = us_since(e);
+  e->pool->work();  // the calling thread widens too
   e->pool->finish();
+  e->last_us[1] = e->pool->first_chunk_us();
+  e->last_us[2] = e->pool->last_chunk_us();
+  e->last_us[3] = us_since(e);
   return PGM_OK;
 }
 
@@ -744,7 +762,8 @@ int pgm_destroy(pgm_engine* e) {
   delete e->pool;
   if (e->d_stream) cudaFree(e->d_stream);
   if (e->h_stream) cudaFreeHost(e->h_stream);
-  for (cudaEvent_t ev : e->stream_events) cudaEventDestroy(ev);
+  if (e->d_flags) cudaFree(e->d_flags);
+  if (e->h_flags) cudaFreeHost(e->h_flags);
   delete e;
   return PGM_OK;
 }
@@ -946,6 +965,7 @@ int pgm_step(pgm_engine* e, const void* actions_dev, int32_t action_itemsize, vo
   a.rewards = rewards_dev;
   a.terminated = terminated_dev;
   a.truncated = truncated_dev;
+  if (!e->ovr_stream) a.batch_agents = e->batch_single;  // (the packed stream's geometry follows batch_agents)
   int rc = launch(e, a, OP_STEP, (cudaStream_t)stream);
   if (rc != PGM_OK || e->cfg.auto_reset != 2) return rc;
   return enqueue_rebuilds(e, obs_dev, (cudaStream_t)stream);
@@ -997,9 +1017,10 @@ int pgm_set_host_transport(pgm_engine* e, int32_t mode, int32_t num_threads) {
 
 int pgm_host_transport_info(const pgm_engine* e, int64_t* out, int32_t n) {
   if (!e || !out) return fail(PGM_ERR_INVALID, "null argument");
-  const int64_t v[5] = {use_packed(e) ? 1 : 0, e->pool ? e->pool->threads() : 0, e->last_h2d_bytes, e->last_d2h_bytes,
-                        pgm::expand_isa()[0] == 'a' ? (pgm::expand_isa()[3] == '5' ? 2 : 1) : 0};
-  for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
+  const int64_t v[10] = {use_packed(e) ? 1 : 0, e->pool ? e->pool->threads() : 0, e->last_h2d_bytes, e->last_d2h_bytes,
+                         pgm::expand_isa()[0] == 'a' ? (pgm::expand_isa()[3] == '5' ? 2 : 1) : 0,
+                         e->last_us[0], e->last_us[1], e->last_us[2], e->last_us[3], e->last_us[4]};
+  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
   return PGM_OK;
 }
 
@@ -1025,6 +1046,7 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
   cudaStream_t s = (cudaStream_t)stream;
   const size_t NA = (size_t)e->cfg.num_envs * e->cfg.num_agents;
   const bool packed = obs_host && use_packed(e);
+  e->t_call = std::chrono::steady_clock::now();
   if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
   if (packed) begin_expand(e, obs_host);  // wake the host threads under the upload + kernel
   CUDA_TRY(cudaMemcpyAsync(e->d_act_h, actions_host, NA * action_itemsize, cudaMemcpyHostToDevice, s));
@@ -1048,6 +1070,7 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
   CUDA_TRY(cudaMemcpyAsync(truncated_host, e->d_trunc_h, NA, cudaMemcpyDeviceToHost, s));
   if (packed && (rc = drain_expand(e)) != PGM_OK) return rc;
   CUDA_TRY(cudaStreamSynchronize(s));
+  e->last_us[4] = us_since(e);
   return PGM_OK;
 }
 

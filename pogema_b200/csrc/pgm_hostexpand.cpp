@@ -5,10 +5,12 @@
 #include "pgm_hostexpand.h"
 
 #include <immintrin.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -147,24 +149,41 @@ struct ExpandPool::Impl {
   std::vector<std::thread> workers;
   std::mutex mu;
   std::condition_variable cv_start, cv_done;
-  uint64_t generation = 0;
-  bool stop = false;
-  int running = 0;
+  std::atomic<uint64_t> generation{0};
+  std::atomic<bool> stop{false};
+  std::atomic<int> running{0};
+  std::atomic<bool> aborted{false};
+  std::chrono::steady_clock::time_point t_begin;
+  std::atomic<int64_t> first_flag_us{-1}, last_flag_us{-1};  // when a thread first saw chunk 0 / the last chunk complete
+  int spin_us = 0;  // a worker polls this long for the next job before it sleeps (the wake-up hides under the
+                    // upload + kernel + first chunk anyway; polling only pays when cores are to spare)
   ExpandJob job;
   int64_t grain = 1;
   alignas(64) std::atomic<int64_t> next{0};
-  alignas(64) std::atomic<int64_t> ready{0};
 
   void run_job() {
     const ExpandJob& j = job;
+    int c = 0;  // chunk of the last unit claimed (claims only move forward)
     for (;;) {
       const int64_t u0 = next.fetch_add(grain, std::memory_order_relaxed);
       if (u0 >= j.units) break;
       const int64_t u1 = std::min(j.units, u0 + grain);
-      int spins = 0;
-      while (ready.load(std::memory_order_acquire) < u1) {
-        if (++spins < 2000) _mm_pause();
-        else std::this_thread::yield();
+      if (j.flags != nullptr) {
+        while (j.units * (c + 1) / j.chunks < u1) ++c;
+        // chunks land in order; x86 does not reorder the data loads before this flag load
+        for (int spins = 0; j.flags[c] != j.flag_value && !aborted.load(std::memory_order_relaxed); ++spins) {
+          if (spins < 4000) _mm_pause();
+          else std::this_thread::yield();
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if ((c == 0 && first_flag_us.load(std::memory_order_relaxed) < 0) ||
+            (c == j.chunks - 1 && last_flag_us.load(std::memory_order_relaxed) < 0)) {
+          const int64_t us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count();
+          int64_t unset = -1;
+          if (c == 0) first_flag_us.compare_exchange_strong(unset, us, std::memory_order_relaxed);
+          unset = -1;
+          if (c == j.chunks - 1) last_flag_us.compare_exchange_strong(unset, us, std::memory_order_relaxed);
+        }
       }
       for (int64_t u = u0; u < u1; ++u) {
         const uint8_t* s = j.src + u * j.src_unit_stride;
@@ -184,23 +203,31 @@ struct ExpandPool::Impl {
   void worker() {
     uint64_t seen = 0;
     for (;;) {
-      {
-        std::unique_lock<std::mutex> lk(mu);
-        cv_start.wait(lk, [&] { return stop || generation != seen; });
-        if (stop) return;
-        seen = generation;
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int i = 0; generation.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed); ++i) {
+        _mm_pause();
+        if ((i & 63) == 63 &&
+            std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= spin_us)
+          break;
       }
+      if (generation.load(std::memory_order_acquire) == seen) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_start.wait(lk, [&] { return stop.load() || generation.load() != seen; });
+      }
+      if (stop.load()) return;
+      seen = generation.load(std::memory_order_acquire);
       run_job();
-      {
+      if (running.fetch_sub(1, std::memory_order_acq_rel) == 1) {
         std::lock_guard<std::mutex> lk(mu);
-        if (--running == 0) cv_done.notify_all();
+        cv_done.notify_all();
       }
     }
   }
 };
 
 ExpandPool::ExpandPool(int threads) : impl_(new Impl()), nthreads_(std::max(1, threads)) {
-  for (int i = 0; i < nthreads_; ++i) impl_->workers.emplace_back([this] { impl_->worker(); });
+  if (const char* v = getenv("PGM_HOST_SPIN_US")) impl_->spin_us = std::max(0, atoi(v));
+  for (int i = 0; i + 1 < nthreads_; ++i) impl_->workers.emplace_back([this] { impl_->worker(); });
 }
 
 ExpandPool::~ExpandPool() {
@@ -221,17 +248,31 @@ void ExpandPool::begin(const ExpandJob& job) {
   impl_->grain = std::max<int64_t>(1, std::min<int64_t>((64 * 1024) / unit_bytes,
                                                           (job.units + 4 * nthreads_ - 1) / (4 * nthreads_)));
   impl_->next.store(0, std::memory_order_relaxed);
-  impl_->ready.store(0, std::memory_order_relaxed);
-  impl_->running = nthreads_;
-  impl_->generation++;
+  impl_->aborted.store(false, std::memory_order_relaxed);
+  impl_->t_begin = std::chrono::steady_clock::now();
+  impl_->first_flag_us.store(-1, std::memory_order_relaxed);
+  impl_->last_flag_us.store(-1, std::memory_order_relaxed);
+  impl_->running.store(nthreads_ - 1, std::memory_order_relaxed);
+  impl_->generation.fetch_add(1, std::memory_order_release);
   impl_->cv_start.notify_all();
 }
 
-void ExpandPool::publish(int64_t ready_units) { impl_->ready.store(ready_units, std::memory_order_release); }
+void ExpandPool::work() { impl_->run_job(); }
+int64_t ExpandPool::first_chunk_us() const { return impl_->first_flag_us.load(); }
+int64_t ExpandPool::last_chunk_us() const { return impl_->last_flag_us.load(); }
+void ExpandPool::abort() { impl_->aborted.store(true, std::memory_order_relaxed); }
 
 void ExpandPool::finish() {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; impl_->running.load(std::memory_order_acquire) != 0; ++i) {
+    _mm_pause();
+    if ((i & 63) == 63 &&
+        std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= 2000)
+      break;
+  }
+  if (impl_->running.load(std::memory_order_acquire) == 0) return;
   std::unique_lock<std::mutex> lk(impl_->mu);
-  impl_->cv_done.wait(lk, [&] { return impl_->running == 0; });
+  impl_->cv_done.wait(lk, [&] { return impl_->running.load() == 0; });
 }
 
 }  // namespace pgm

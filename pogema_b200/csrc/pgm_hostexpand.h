@@ -27,6 +27,12 @@ struct ExpandJob {
   int64_t batch_elems = 0;       // elements (= bits) per full batch
   int64_t unit_elems = 0;        // elements per instance
   int elem_size = 1;
+  // Arrival of the stream: chunk c = units [units*c/chunks, units*(c+1)/chunks) is complete once
+  // flags[c] == flag_value (the copy engine writes the flag right after the chunk, in stream order).
+  // flags == nullptr: everything is already there.
+  const volatile uint32_t* flags = nullptr;
+  uint32_t flag_value = 0;
+  int chunks = 1;
 };
 
 class ExpandPool {
@@ -34,10 +40,13 @@ class ExpandPool {
   explicit ExpandPool(int threads);
   ~ExpandPool();
   int threads() const { return nthreads_; }
-  // begin(): wake the workers; they expand units as publish() makes them available.
-  void begin(const ExpandJob& job);
-  void publish(int64_t ready_units);  // units [0, ready_units) of src are complete
-  void finish();                      // returns when every unit has been expanded (sfence'd)
+  // `threads` counts the calling thread: threads - 1 workers are started, the caller joins in through work().
+  void begin(const ExpandJob& job);  // wake the workers; they widen chunks as their flags arrive
+  void work();                       // the calling thread widens units too, until none is left to claim
+  void abort();                      // stop waiting for flags (a failed launch): units are processed as they are
+  void finish();                     // returns when every unit has been widened (sfence'd)
+  int64_t first_chunk_us() const;    // microseconds after begin() at which chunk 0 / the last chunk was seen complete
+  int64_t last_chunk_us() const;
  private:
   struct Impl;
   Impl* impl_;

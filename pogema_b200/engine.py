@@ -150,10 +150,12 @@ class Engine:
         nat.check(self.lib.pgm_set_host_transport(self.handle, m, int(num_threads)))
 
     def host_transport_info(self) -> dict:
-        out = (C.c_int64 * 5)()
-        nat.check(self.lib.pgm_host_transport_info(self.handle, out, 5))
+        out = (C.c_int64 * 10)()
+        nat.check(self.lib.pgm_host_transport_info(self.handle, out, 10))
         return {"packed": bool(out[0]), "threads": int(out[1]), "h2d_bytes": int(out[2]), "d2h_bytes": int(out[3]),
-                "isa": ["scalar", "avx2", "avx512bw"][int(out[4])]}
+                "isa": ["scalar", "avx2", "avx512bw"][int(out[4])],
+                "timeline_us": dict(zip(("enqueued", "first_chunk", "last_chunk", "widened", "returned"),
+                                        [int(v) for v in out[5:10]]))}
 
     def observe_host(self, stream: int = 0) -> np.ndarray:
         """Observation of the current state as a host array (pgm_observe_host)."""

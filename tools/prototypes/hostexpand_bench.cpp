@@ -18,10 +18,10 @@ int main(int argc, char** argv) {
   pgm::ExpandJob j;
   j.src = src.data(); j.dst = dst; j.units = N; j.src_unit_stride = sstride; j.dst_unit_stride = bits * es;
   j.batches = 1; j.src_batch_stride = sstride; j.batch_elems = bits; j.unit_elems = bits; j.elem_size = es;
-  for (int it = 0; it < 3; ++it) { pool.begin(j); pool.publish(N); pool.finish(); }
+  for (int it = 0; it < 3; ++it) { pool.begin(j); pool.work(); pool.finish(); }
   auto t0 = std::chrono::steady_clock::now();
   const int iters = 20;
-  for (int it = 0; it < iters; ++it) { pool.begin(j); pool.publish(N); pool.finish(); }
+  for (int it = 0; it < iters; ++it) { pool.begin(j); pool.work(); pool.finish(); }
   double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / iters;
   printf("isa %s threads %d elem %d: %.3f ms per tensor (%.1f MB) = %.1f GB/s written, %.1f M agent-steps/s\n",
          pgm::expand_isa(), threads, es, dt * 1e3, N * bits * es / 1e6, N * bits * es / dt / 1e9, N * 64 / dt / 1e6);
