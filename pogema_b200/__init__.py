@@ -21,9 +21,12 @@ def __getattr__(name):
     if name == "Engine":
         from .engine import Engine
         return Engine
-    if name in ("pogema_v0", "make_pogema", "Pogema", "PogemaLifeLong", "PogemaCoopFinish", "AnimationMonitor"):
+    if name in ("pogema_v0", "make_pogema", "Pogema", "PogemaLifeLong", "PogemaCoopFinish"):
         from . import envs
         return getattr(envs, name)
+    if name in ("AnimationMonitor", "AnimationConfig", "PersistentWrapper", "AgentState", "AutoResetWrapper"):
+        from . import wrappers
+        return getattr(wrappers, name)
     if name == "parallel_env":
         from .integrations.pettingzoo import parallel_env
         return parallel_env

@@ -336,7 +336,11 @@ PogemaCoopFinish = Pogema
 
 
 def _make_pogema(grid_config):
-    return Pogema(grid_config)
+    env = Pogema(grid_config)
+    if grid_config.persistent:  # upstream integrations/make_pogema.py :: _make_pogema
+        from .wrappers import PersistentWrapper
+        env = PersistentWrapper(env)
+    return env
 
 
 def make_pogema(grid_config=None, *args, **kwargs):
