@@ -199,9 +199,10 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     A = WORKLOAD["num_agents"]
-    inst_per_core = 8
-    # one bench "step" = one oracle step over cores*inst_per_core instances (a bounded sample of the workload)
+    # one bench "step" = one oracle step over cores*inst_per_core instances (a bounded sample of the workload),
+    # sized for ~6 s per process at ~200 k agent-steps/s/core so that short runs are not dominated by noise
     n_steps = args.steps
+    inst_per_core = int(min(256, max(8, -(-6 * 200_000 // (max(n_steps, 1) * A)))))
     t_rate, total, slowest, wall = oracle_throughput(cores, inst_per_core, n_steps, n_warm=args.warmup)
     sample = (f"{cores} processes x {inst_per_core} instances of the workload shape x {n_steps} steps "
               f"({total} agent-steps, slowest process {slowest:.1f} s), Python/numpy restatement of upstream pogema")

@@ -347,11 +347,9 @@ StepArgs make_args(pgm_engine* e) {
   a.obs_slot_stride = 0;
   a.obs = nullptr;
   a.obs_inst_stride = e->obs_inst_stride;
-  a.stream_batch_bytes = 0;
   if (e->ovr_stream) {
     a.obs_format = 3;
     a.obs_inst_stride = e->stream_unit_bytes;
-    a.stream_batch_bytes = (int)e->stream_batch_bytes;
   }
   a.rewards = nullptr;
   a.terminated = nullptr;
@@ -545,10 +543,12 @@ bool use_packed(const pgm_engine* e) {
 
 int ensure_stream(pgm_engine* e) {
   if (!e->d_stream) {
+    // geometry of obs_format 3 (pgm_kernels.cuh): batch b of an instance starts at the word its first agent would
+    // have in the bits format (ceil(bits_per_agent / 32) words per agent); inside a batch the agents are bit-contiguous
     const int64_t A = e->cfg.num_agents, g = e->batch_agents;
-    const int64_t batches = (A + g - 1) / g;
-    e->stream_batch_bytes = (int64_t)round_up((int)((g * e->bits_per_agent + 31) / 32), 4) * 4;
-    e->stream_unit_bytes = batches * e->stream_batch_bytes;
+    const int64_t wpa = (e->bits_per_agent + 31) / 32;
+    e->stream_batch_bytes = g * wpa * 4;
+    e->stream_unit_bytes = A * wpa * 4;
     e->stream_bytes = e->stream_unit_bytes * e->cfg.num_envs;
     CUDA_TRY(cudaMalloc((void**)&e->d_stream, (size_t)e->stream_bytes + 64));
     CUDA_TRY(cudaHostAlloc((void**)&e->h_stream, (size_t)e->stream_bytes + 64, cudaHostAllocDefault));

@@ -47,8 +47,8 @@ struct StepArgs {
   int bits_per_agent;   // 3*D*D
   int stage_bpa;        // stage bits per agent: bits_per_agent (U8) or rounded up to 32 (BITS)
   int obs_format;       // 0 u8, 1 bits, 2 float32, 3 raw stream (packed host transport: the stage bit stream of
-                        // every observation batch as it is, batches stream_batch_bytes apart)
-  int stream_batch_bytes;
+                        // every observation batch as it is; a batch starts where its first agent's words
+                        // would start in format 1)
   int max_steps, auto_reset;
   int on_target;        // 0 finish, 1 nothing, 2 restart
   int batch_agents;     // agents per observation batch (stage capacity)
@@ -383,16 +383,14 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* 
     team_sync<TEAM>(bar_id);
     PGM_STAMP(7);
     // ---- write out
-    if (p.obs_format == 3) {
-      // packed host transport (pgm_step_host): the bit stream itself, 16-byte stores; the host widens it
-      uint4* out = reinterpret_cast<uint4*>(obs + (long long)n * p.obs_inst_stride +
-                                            (long long)(g0 / p.batch_agents) * p.stream_batch_bytes);
-      const int nv = ((nbits + 31) / 32 + 3) >> 2;
-      for (int w = tid; w < nv; w += TEAM) __stcs(out + w, stage4[w]);
-    } else if (p.obs_format == 1) {
-      const int wpa = sbpa >> 5;
+    if (p.obs_format & 1) {
+      // 1: bits, 32-bit words per agent.  3 (packed host transport, pgm_step_host): the stage bit stream of the
+      // batch as it is (agents bit-contiguous); batch b starts at the word offset agent b*batch would have in
+      // format 1, so both formats share this loop.
+      const int wpa = (bpa + 31) >> 5;
       uint32_t* out = reinterpret_cast<uint32_t*>(obs + (long long)n * p.obs_inst_stride) + (long long)g0 * wpa;
-      for (int w = tid; w < gcount * wpa; w += TEAM) __stcs(out + w, stage[w]);
+      const int nw = (nbits + 31) >> 5;
+      for (int w = tid; w < nw; w += TEAM) __stcs(out + w, stage[w]);
     } else if (p.obs_format == 2) {
       // float32 0.0 / 1.0 (the reference's observation dtype): one stream bit -> one float, 16-byte stores
       float* out = reinterpret_cast<float*>(obs + (long long)n * p.obs_inst_stride) + (long long)g0 * bpa;

@@ -12,13 +12,14 @@ ap.add_argument("--mode", default="packed")
 ap.add_argument("--fmt", default="u8")
 ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--pageable", action="store_true")
+ap.add_argument("--size", type=int, default=32); ap.add_argument("--agents", type=int, default=64); ap.add_argument("--r", type=int, default=5)
 a = ap.parse_args()
-gc = GridConfig(size=32, density=0.3, num_agents=64, obs_radius=5, max_episode_steps=64, collision_system="priority", on_target="finish")
+gc = GridConfig(size=a.size, density=0.3, num_agents=a.agents, obs_radius=a.r, max_episode_steps=64, collision_system="priority", on_target="finish")
 env = BatchedPogema(gc, num_envs=a.n, auto_reset=True, obs_format=a.fmt)
 env.reset()
 e = env.engine
 e.set_host_transport(a.mode, a.threads)
-N, A = a.n, 64
+N, A = a.n, a.agents
 pin = (lambda t: t) if a.pageable else (lambda t: t.pin_memory())
 h_act = [pin(torch.randint(0, 5, (N, A), dtype=torch.uint8)) for _ in range(4)]
 h_obs = pin(torch.empty(e.obs_shape(), dtype=torch.float32 if a.fmt == "f32" else torch.uint8))

@@ -14,3 +14,8 @@ compute-sanitizer --tool memcheck --error-exitcode 9 python tools/quick_bench.py
 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/quick_bench.py --n 6 --size 300 --agents 40 --r 5 --coll soft --ot restart --steps 4 --max-steps 5 > gpurun_out/san_memcheck_buckets.log 2>&1; echo "memcheck tile-buckets exit=$?"; tail -2 gpurun_out/san_memcheck_buckets.log
 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/quick_bench.py --n 6 --size 300 --agents 40 --r 5 --coll priority --ot finish --steps 4 --max-steps 5 > gpurun_out/san_racecheck_buckets.log 2>&1; echo "racecheck tile-buckets exit=$?"; tail -2 gpurun_out/san_racecheck_buckets.log
 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/quick_bench.py --n 24 --size 40 --agents 300 --r 5 --coll priority --ot finish --steps 4 --max-steps 5 > gpurun_out/san_racecheck_team.log 2>&1; echo "racecheck big-team exit=$?"; tail -2 gpurun_out/san_racecheck_team.log
+# single-step launches with two observation batches (64 agents on a warp), and the packed host transport (obs_format 3 + flag copies)
+compute-sanitizer --tool racecheck --error-exitcode 9 python tools/quick_bench.py --n 24 --size 16 --agents 64 --r 3 --steps 6 --max-steps 5 > gpurun_out/san_racecheck_twobatch.log 2>&1; echo "racecheck two-batch exit=$?"; tail -2 gpurun_out/san_racecheck_twobatch.log
+for tool in memcheck racecheck initcheck; do
+  compute-sanitizer --tool $tool --error-exitcode 9 python tools/e2e_probe.py --n 40 --size 12 --agents 20 --r 3 --steps 6 --threads 3 > gpurun_out/san_${tool}_packed.log 2>&1; echo "$tool packed exit=$?"; tail -2 gpurun_out/san_${tool}_packed.log
+done
