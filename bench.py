@@ -219,7 +219,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line at the
+    first communicator): keep the real stdout for the result and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def run_cuda(args):
+    out = _claim_stdout()
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -458,7 +468,7 @@ def run_cuda(args):
                 # context only: a plain-C restatement of the same path (not how the reference is implemented)
                 line["cpu_baseline_c"] = {"value": c_res[0], "unit": UNIT, "cores": cores, "kind": "port (C, oracle/step_oracle.c)",
                                           "sample": f"{cores} processes x 32 instances for ~4 s ({c_res[1]} agent-steps)"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
