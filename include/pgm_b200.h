@@ -204,6 +204,17 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
                   float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host,
                   void* stream);
 
+/*
+ * pgm_step_host plus the two per-agent flags upstream keeps beside the step results, in the same
+ * synchronisation: active_host uint8 [N][A] = upstream grid.py :: Grid.is_active after the step,
+ * was_on_goal_host uint8 [N][A] = upstream envs.py :: Pogema.was_on_goal.  Either may be NULL.
+ * (The list API needs both every step for `infos`; asking for them here instead of through two
+ * pgm_get_state calls takes a single-instance step from 124 us to well under half of that.)
+ */
+int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_itemsize, void* obs_host,
+                     float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                     uint8_t* active_host, uint8_t* was_on_goal_host, void* stream);
+
 /* upstream Pogema._obs with a HOST destination buffer (copies device->host, synchronises). */
 int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream);
 

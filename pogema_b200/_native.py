@@ -23,7 +23,7 @@ STATE_POSITIONS, STATE_TARGETS, STATE_ACTIVE, STATE_ELAPSED, STATE_OBSTACLES, ST
 EXPORTS = [
     "pgm_last_error", "pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_obs_bytes",
     "pgm_obs_instance_stride", "pgm_generate", "pgm_generate_device", "pgm_generate_host", "pgm_set_tasks", "pgm_reset", "pgm_observe", "pgm_step",
-    "pgm_step_many", "pgm_step_host", "pgm_observe_host", "pgm_get_state", "pgm_state_ptr", "pgm_checkpoint_bytes", "pgm_checkpoint_save",
+    "pgm_step_many", "pgm_step_host", "pgm_step_host_ex", "pgm_observe_host", "pgm_get_state", "pgm_state_ptr", "pgm_checkpoint_bytes", "pgm_checkpoint_save",
     "pgm_checkpoint_load", "pgm_check_errors", "pgm_launch_count", "pgm_plan", "pgm_set_debug_buffer",
     "pgm_set_host_transport", "pgm_host_transport_info", "pgm_expand_bits_host",
 ]
@@ -73,6 +73,7 @@ def load():
     lib.pgm_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     lib.pgm_step_many.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp]
     lib.pgm_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.pgm_step_host_ex.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.pgm_observe_host.argtypes = [vp, vp, vp]
     lib.pgm_get_state.argtypes = [vp, i32, vp, i64, vp]
     lib.pgm_state_ptr.argtypes = [vp, i32]

@@ -83,6 +83,11 @@ struct pgm_engine {
   uint8_t *d_act_h = nullptr, *d_obs_h = nullptr, *d_term_h = nullptr, *d_trunc_h = nullptr;
   float* d_rew_h = nullptr;
   int act_h_itemsize = 0;
+  // d_obs_h / d_rew_h / d_term_h / d_trunc_h are parts of ONE device block (d_obs_h is its base); small results
+  // (single instances behind the list API) come back with one copy into pinned staging and one synchronisation
+  int64_t out_block_bytes = 0, off_rew = 0, off_term = 0, off_trunc = 0;
+  uint8_t* h_small = nullptr;  // pinned: [block | state NA*8 | was NA], only if the block is <= kSmallBlock
+  std::vector<uint2> h_state_tmp;
   // host mirrors
   std::vector<uint32_t> h_obst;
   bool h_obst_valid = true;  // false after a device-side generation (obstacles are read back on demand)
@@ -443,13 +448,22 @@ int dev_alloc(T** p, size_t n) {
   return PGM_OK;
 }
 
+constexpr int64_t kSmallBlock = 256 * 1024;
+
 int ensure_host_scratch(pgm_engine* e, int itemsize) {
   const size_t NA = (size_t)e->cfg.num_envs * e->cfg.num_agents;
   if (!e->d_obs_h) {
-    CUDA_TRY(cudaMalloc((void**)&e->d_obs_h, (size_t)e->obs_bytes));
-    CUDA_TRY(cudaMalloc((void**)&e->d_rew_h, NA * 4));
-    CUDA_TRY(cudaMalloc((void**)&e->d_term_h, NA));
-    CUDA_TRY(cudaMalloc((void**)&e->d_trunc_h, NA));
+    auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
+    e->off_rew = up(e->obs_bytes);
+    e->off_term = e->off_rew + up((int64_t)NA * 4);
+    e->off_trunc = e->off_term + up((int64_t)NA);
+    e->out_block_bytes = e->off_trunc + up((int64_t)NA);
+    CUDA_TRY(cudaMalloc((void**)&e->d_obs_h, (size_t)e->out_block_bytes));
+    e->d_rew_h = (float*)(e->d_obs_h + e->off_rew);
+    e->d_term_h = e->d_obs_h + e->off_term;
+    e->d_trunc_h = e->d_obs_h + e->off_trunc;
+    if (e->out_block_bytes <= kSmallBlock)
+      CUDA_TRY(cudaHostAlloc((void**)&e->h_small, (size_t)e->out_block_bytes + NA * 9, cudaHostAllocDefault));
   }
   if (e->act_h_itemsize < itemsize) {
     if (e->d_act_h) cudaFree(e->d_act_h);
@@ -755,13 +769,14 @@ int pgm_destroy(pgm_engine* e) {
   DeviceGuard guard(e->cfg.device);
   void* ptrs[] = {e->d_obst,  e->d_state, e->d_state0, e->d_was,
                   e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
-                  e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h, e->d_term_h, e->d_trunc_h,
-                  e->d_rew_h, e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count};
+                  e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h /* base of the result block */,
+                  e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e->pool;
   if (e->d_stream) cudaFree(e->d_stream);
   if (e->h_stream) cudaFreeHost(e->h_stream);
+  if (e->h_small) cudaFreeHost(e->h_small);
   if (e->d_flags) cudaFree(e->d_flags);
   if (e->h_flags) cudaFreeHost(e->h_flags);
   delete e;
@@ -1036,6 +1051,13 @@ int pgm_expand_bits_host(const uint32_t* src_host, int64_t nbits, void* dst_host
 
 int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsize, void* obs_host,
                   float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream) {
+  return pgm_step_host_ex(e, actions_host, action_itemsize, obs_host, rewards_host, terminated_host, truncated_host,
+                          nullptr, nullptr, stream);
+}
+
+int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_itemsize, void* obs_host,
+                     float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host, uint8_t* active_host,
+                     uint8_t* was_on_goal_host, void* stream) {
   if (!e || !actions_host || !rewards_host || !terminated_host || !truncated_host)
     return fail(PGM_ERR_INVALID, "null argument");
   if (action_itemsize != 1 && action_itemsize != 2 && action_itemsize != 4 && action_itemsize != 8)
@@ -1046,6 +1068,7 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
   cudaStream_t s = (cudaStream_t)stream;
   const size_t NA = (size_t)e->cfg.num_envs * e->cfg.num_agents;
   const bool packed = obs_host && use_packed(e);
+  const bool small = !packed && e->h_small != nullptr;
   e->t_call = std::chrono::steady_clock::now();
   if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
   if (packed) begin_expand(e, obs_host);  // wake the host threads under the upload + kernel
@@ -1059,17 +1082,43 @@ int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsi
     return rc;
   }
   e->last_h2d_bytes = (int64_t)(NA * action_itemsize);
-  e->last_d2h_bytes = (int64_t)(NA * 6) + (obs_host ? (packed ? e->stream_bytes : e->obs_bytes) : 0);
-  if (packed) {
-    if ((rc = enqueue_stream_copies(e, s)) != PGM_OK) return rc;
-  } else if (obs_host) {
-    CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+  e->last_d2h_bytes = (int64_t)(NA * 6) + (obs_host ? (packed ? e->stream_bytes : e->obs_bytes) : 0) +
+                      (active_host ? (int64_t)NA * 8 : 0) + (was_on_goal_host ? (int64_t)NA : 0);
+  const uint2* state_host = nullptr;
+  if (small) {
+    // a single instance behind the list API: everything in three async copies into pinned staging, one wait
+    // (five separate copies into pageable buffers cost ~12 us each, more than the step itself)
+    uint8_t* st = e->h_small + e->out_block_bytes;
+    CUDA_TRY(cudaMemcpyAsync(e->h_small, e->d_obs_h, (size_t)e->out_block_bytes, cudaMemcpyDeviceToHost, s));
+    if (active_host) CUDA_TRY(cudaMemcpyAsync(st, e->d_state, NA * 8, cudaMemcpyDeviceToHost, s));
+    if (was_on_goal_host) CUDA_TRY(cudaMemcpyAsync(st + NA * 8, e->d_was, NA, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (obs_host) memcpy(obs_host, e->h_small, (size_t)e->obs_bytes);
+    memcpy(rewards_host, e->h_small + e->off_rew, NA * 4);
+    memcpy(terminated_host, e->h_small + e->off_term, NA);
+    memcpy(truncated_host, e->h_small + e->off_trunc, NA);
+    if (was_on_goal_host) memcpy(was_on_goal_host, st + NA * 8, NA);
+    state_host = reinterpret_cast<const uint2*>(st);
+  } else {
+    if (packed) {
+      if ((rc = enqueue_stream_copies(e, s)) != PGM_OK) return rc;
+    } else if (obs_host) {
+      CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(rewards_host, e->d_rew_h, NA * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(terminated_host, e->d_term_h, NA, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(truncated_host, e->d_trunc_h, NA, cudaMemcpyDeviceToHost, s));
+    if (active_host) {
+      e->h_state_tmp.resize(NA);
+      CUDA_TRY(cudaMemcpyAsync(e->h_state_tmp.data(), e->d_state, NA * 8, cudaMemcpyDeviceToHost, s));
+      state_host = e->h_state_tmp.data();
+    }
+    if (was_on_goal_host) CUDA_TRY(cudaMemcpyAsync(was_on_goal_host, e->d_was, NA, cudaMemcpyDeviceToHost, s));
+    if (packed && (rc = drain_expand(e)) != PGM_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
   }
-  CUDA_TRY(cudaMemcpyAsync(rewards_host, e->d_rew_h, NA * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(terminated_host, e->d_term_h, NA, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(truncated_host, e->d_trunc_h, NA, cudaMemcpyDeviceToHost, s));
-  if (packed && (rc = drain_expand(e)) != PGM_OK) return rc;
-  CUDA_TRY(cudaStreamSynchronize(s));
+  if (active_host)
+    for (size_t i = 0; i < NA; ++i) active_host[i] = (uint8_t)((state_host[i].x >> 15) & 1u);
   e->last_us[4] = us_since(e);
   return PGM_OK;
 }

@@ -136,11 +136,15 @@ class Engine:
         return {"bits": np.uint32, "f32": np.float32}.get(self.obs_format, np.uint8)
 
     def step_host(self, actions: np.ndarray, obs: Optional[np.ndarray], rewards: np.ndarray,
-                  terminated: np.ndarray, truncated: np.ndarray, stream: int = 0):
+                  terminated: np.ndarray, truncated: np.ndarray, stream: int = 0,
+                  active: Optional[np.ndarray] = None, was_on_goal: Optional[np.ndarray] = None):
+        """pgm_step_host / pgm_step_host_ex: one step with host buffers; ``active`` / ``was_on_goal`` (uint8 [N, A],
+        optional) receive upstream's ``grid.is_active`` / ``env.was_on_goal`` in the same synchronisation."""
         actions = np.ascontiguousarray(actions)
         assert actions.size == self.num_envs * self.num_agents
-        nat.check(self.lib.pgm_step_host(self.handle, _ptr(actions), actions.itemsize, _ptr(obs), _ptr(rewards),
-                                         _ptr(terminated), _ptr(truncated), C.c_void_p(stream)))
+        nat.check(self.lib.pgm_step_host_ex(self.handle, _ptr(actions), actions.itemsize, _ptr(obs), _ptr(rewards),
+                                            _ptr(terminated), _ptr(truncated), _ptr(active), _ptr(was_on_goal),
+                                            C.c_void_p(stream)))
 
     def set_host_transport(self, mode="auto", num_threads: int = 0):
         """How step_host / observe_host bring observations to the host (pgm_set_host_transport):

@@ -214,6 +214,8 @@ class Pogema(_Base):
             self._h_rew = np.empty((n, a), dtype=np.float32)
             self._h_term = np.empty((n, a), dtype=np.uint8)
             self._h_trunc = np.empty((n, a), dtype=np.uint8)
+            self._h_active = np.ones((n, a), dtype=np.uint8)
+            self._h_was = np.zeros((n, a), dtype=np.uint8)
         self._engine.grid_config = gc
 
     def _obs_list(self, obs_u8):
@@ -222,7 +224,7 @@ class Pogema(_Base):
         n = self.grid_config.num_agents
         kind = self.grid_config.observation_type
         if kind == 'default':
-            return [obs_u8[0, i].astype(np.float32) for i in range(n)]
+            return list(obs_u8[0].astype(np.float32))  # one conversion; fresh arrays every step like upstream
         pos = self._engine.get_state(nat.STATE_POSITIONS)[0]
         tgt = self._engine.get_state(nat.STATE_TARGETS)[0]
         start = self._initial_xy
@@ -241,9 +243,10 @@ class Pogema(_Base):
                 results[i]['global_target_xy'] = (int(tgt[i][0]) + r, int(tgt[i][1]) + r)
         return results
 
-    def _get_infos(self):
-        active = self._engine.get_state(nat.STATE_ACTIVE)[0]
-        return [dict(is_active=bool(active[i])) for i in range(self.grid_config.num_agents)]
+    def _get_infos(self, active=None):
+        if active is None:
+            active = self._engine.get_state(nat.STATE_ACTIVE)[0]
+        return [dict(is_active=bool(v)) for v in active]
 
     # -- gymnasium style API ------------------------------------------------ #
     def reset(self, seed: Optional[int] = None, return_info: bool = True, options: Optional[dict] = None):
@@ -271,14 +274,15 @@ class Pogema(_Base):
         if act.size and (act.min() < 0 or act.max() >= self.action_space.n):
             raise IndexError("action out of range [0, %d)" % self.action_space.n)
         act = np.ascontiguousarray(act.astype(np.uint8).reshape(1, -1))
-        self._engine.step_host(act, self._h_obs, self._h_rew, self._h_term, self._h_trunc)
+        # one C-ABI call, one synchronisation: results plus upstream's is_active / was_on_goal flags
+        self._engine.step_host(act, self._h_obs, self._h_rew, self._h_term, self._h_trunc,
+                               active=self._h_active, was_on_goal=self._h_was)
         self._elapsed_steps += 1
-        n = self.grid_config.num_agents
-        rewards = [float(self._h_rew[0, i]) for i in range(n)]
-        terminated = [bool(self._h_term[0, i]) for i in range(n)]
-        truncated = [bool(self._h_trunc[0, i]) for i in range(n)]
-        self.was_on_goal = [bool(v) for v in self._engine.get_state(nat.STATE_WAS_ON_GOAL)[0]]
-        infos = self._get_infos()
+        rewards = self._h_rew[0].tolist()
+        terminated = self._h_term[0].astype(bool).tolist()
+        truncated = self._h_trunc[0].astype(bool).tolist()
+        self.was_on_goal = self._h_was[0].astype(bool).tolist()
+        infos = self._get_infos(self._h_active[0])
         obs = self._obs_list(self._h_obs)
         if all(truncated) or all(terminated):
             infos[0]['metrics'] = self._episode_metrics()

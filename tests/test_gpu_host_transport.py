@@ -95,3 +95,33 @@ def test_packed_transport_rejected_for_bits_and_auto_threshold():
     assert not small.engine.host_transport_info()["packed"]            # auto: tiny tensors use the plain DMA
     big = BatchedPogema(GridConfig(size=16, density=0.2, num_agents=32, obs_radius=5, seed=1), num_envs=512)
     assert big.engine.host_transport_info()["packed"]                  # 5.9 MB of observations
+
+
+@pytest.mark.parametrize("envs,mode", [(1, "auto"), (3, "auto"), (700, "plain"), (700, "packed")])
+def test_step_host_ex_flags_match_state(envs, mode):
+    """pgm_step_host_ex: is_active / was_on_goal arrive with the step results (single small copy for tiny engines,
+    separate copies for large ones) and equal what pgm_get_state reports afterwards."""
+    from pogema_b200 import BatchedPogema, GridConfig
+    from pogema_b200 import _native as nat
+    gc = GridConfig(size=10, density=0.2, num_agents=7, obs_radius=5, max_episode_steps=40, collision_system="soft",
+                    on_target="finish", seed=2)
+    a = BatchedPogema(gc, num_envs=envs, auto_reset=False)
+    b = BatchedPogema(gc, num_envs=envs, auto_reset=False)
+    a.engine.set_host_transport(mode)
+    a.reset(), b.reset()
+    acts = make_actions(30, envs, 7, seed=9)
+    obs, rew, te, tr = _host_bufs(a.engine)
+    active = np.full((envs, 7), 9, np.uint8)
+    was = np.full((envs, 7), 9, np.uint8)
+    import torch
+    for t in range(acts.shape[0]):
+        a.engine.step_host(acts[t], obs, rew, te, tr, active=active, was_on_goal=was)
+        o, r, term, trunc = b.step(torch.from_numpy(acts[t]).cuda())
+        assert np.array_equal(obs, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy())
+        assert np.array_equal(te.astype(bool), term.cpu().numpy()) and np.array_equal(tr.astype(bool), trunc.cpu().numpy())
+        assert np.array_equal(active, b.engine.get_state(nat.STATE_ACTIVE))
+        assert np.array_equal(was, b.engine.get_state(nat.STATE_WAS_ON_GOAL))
+    assert active.min() == 0          # some agents finished and disappeared
+    # flags are optional, individually
+    a.engine.step_host(acts[0], None, rew, te, tr, active=active)
+    a.engine.step_host(acts[0], obs, rew, te, tr, was_on_goal=was)
