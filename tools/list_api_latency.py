@@ -1,3 +1,5 @@
+"""Latency of one step through the upstream-style list API (pogema_v0, configs[0]: one 8x8 instance, 4 agents)
+next to the numpy oracle on the same host, and the parts of it (development aid)."""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import numpy as np
@@ -28,5 +30,5 @@ t0 = time.perf_counter()
 for i in range(2000): e.get_state(nat.STATE_WAS_ON_GOAL)
 print("get_state(WAS_ON_GOAL): %.1f us" % ((time.perf_counter() - t0) / 2000 * 1e6))
 t0 = time.perf_counter()
-for i in range(2000): env._obs_list(env._h_obs); env._get_infos()
+for i in range(2000): env._obs_list(env._h_obs); env._get_infos(env._h_active[0])
 print("python list building + infos: %.1f us" % ((time.perf_counter() - t0) / 2000 * 1e6))
