@@ -159,7 +159,8 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   // still lets `want_resident` instances share an SM, but never less than 32 agents (or all of them)
   const long long per_agent_bits = e->stage_bpa;
   auto stage_bytes_for = [&](long long g) { return (long long)round_up((int)(((g * per_agent_bits + 31) / 32 + 2) * 4), 16); };
-  const long long target = smem_max / std::max(1, want_resident);
+  // an SM has 228 KB; every resident CTA costs 1 KB of it on top of its own allocation
+  const long long target = (228 * 1024) / std::max(1, want_resident) - 1024;
   long long budget = std::max<long long>(occ_bytes, target - fixed);
   budget = std::max<long long>(budget, stage_bytes_for(std::min(A, 32)));
   budget = std::min<long long>(budget, (long long)smem_max - fixed);
@@ -167,6 +168,7 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   long long g = (budget >= stage_bytes_for(A)) ? A : ((budget - 16) * 8) / per_agent_bits;
   if (g < 1) return false;
   g = std::min<long long>(g, A);
+  if (g < A && g > 32) g = g / 32 * 32;  // whole warps of agents per batch
   if (const char* v = getenv("PGM_OBS_BATCH")) g = std::max<long long>(1, std::min<long long>(g, atoi(v)));  // tuning knob
   const int stage_bytes = (int)stage_bytes_for(g);
   StepArgs& L = out->L;
@@ -212,15 +214,19 @@ int compute_plan(pgm_engine* e) {
   int per_sm = (c.num_envs + e->sm_count - 1) / e->sm_count;  // instances an SM has to host
   if (const char* v = getenv("PGM_RESIDENT")) per_sm = std::max(1, atoi(v));  // tuning knob
   // Instances an SM should host at a time: what the job needs, but not so many that a team drops
-  // below ~half a thread per agent (measured on 1024-agent instances: 2 x 512 threads beat 4 x 256
-  // and 1 x 1024).  The dense cell->agent grid is used when it reaches that residency (one LDS per
+  // below a quarter of a thread per agent (measured on 512 instances of 1024 agents, 256x256 map: 4 x 256
+  // threads with 128-agent observation batches 42.7 us per step, 2 x 512 threads 48.0, 1 x 1024 56.6 -
+  // four teams per SM interleave their move and store phases, two mostly alternate; 512-agent instances
+  // keep 4 x 256: 7 x 128 threads gain 4 % with 16 steps per launch but lose 16 % with one).  The dense cell->agent grid is used when it reaches that residency (one LDS per
   // lookup), otherwise the tile buckets (memory ~ agents instead of cells).
-  const int want = std::max(1, std::min(per_sm, std::max(2, 2048 / pow2_ceil(A))));
+  int want = std::max(1, std::min(per_sm, std::max(A <= 1024 ? 4 : 2, 2048 / pow2_ceil(A))));
+  if (const char* v = getenv("PGM_WANT")) want = std::max(1, atoi(v));  // tuning knob
   Layout dense, buckets, *use = nullptr;
   const bool ok_d = make_layout(e, 0, want, &dense);
   const bool ok_h = make_layout(e, 1, want, &buckets);
-  const int res_d = ok_d ? std::min(want, smem_max / dense.team_smem) : 0;
-  const int res_h = ok_h ? std::min(want, smem_max / buckets.team_smem) : 0;
+  auto fit = [](int team_smem) { return (228 * 1024) / (team_smem + 1024); };  // 1 KB per resident CTA is reserved
+  const int res_d = ok_d ? std::min(want, fit(dense.team_smem)) : 0;
+  const int res_h = ok_h ? std::min(want, fit(buckets.team_smem)) : 0;
   int force = -1;
   if (const char* v = getenv("PGM_OCC")) force = atoi(v);  // tuning knob: 0 dense grid, 1 tile buckets
   if (force == 0 && ok_d) use = &dense;
@@ -241,7 +247,7 @@ int compute_plan(pgm_engine* e) {
   int team = use->obst_global ? 1024 : c.team_threads;
   if (team == 0) {
     // ~1024 threads per SM (64 registers each) shared by the instances an SM hosts at a time
-    const int resident = std::max(1, std::min(want, smem_max / L.team_smem));
+    const int resident = std::max(1, std::min(want, fit(L.team_smem)));
     team = pow2_floor(std::max(32, 1024 / resident));
     team = std::min(team, std::max(32, pow2_ceil(A)));
     team = std::min(team, 1024);
