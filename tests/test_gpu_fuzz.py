@@ -14,7 +14,9 @@ COLLS = ("priority", "block_both", "soft")
 ONTS = ("finish", "nothing", "restart")
 
 
-def run_both(gc, seeds, T, auto_reset, team, fmt="u8"):
+def run_both(gc, seeds, T, auto_reset, team, fmt="u8", path="device"):
+    """path: 'device' = pgm_step with device pointers; 'plain' / 'packed' = pgm_step_host_ex with host buffers
+    through the plain DMA or the packed transport (GPU-written bit stream, host threads widen it)."""
     import torch
     from pogema_b200 import BatchedPogema, GridConfig
     env = BatchedPogema(GridConfig(**gc), num_envs=len(seeds), seeds=seeds, auto_reset=auto_reset, team_threads=team,
@@ -24,21 +26,32 @@ def run_both(gc, seeds, T, auto_reset, team, fmt="u8"):
     r = gc["obs_radius"]
     actions = make_actions(T, len(seeds), A, seed=hash(str(sorted(gc.items(), key=str))) % 1000)
     obs = env.reset()
-    first = co.run(np.zeros((0, len(seeds), A), np.uint8)) if False else None
+    if path != "device":
+        env.engine.set_host_transport(path, 1 + len(seeds) % 3)
+        n = len(seeds)
+        hb = (np.empty(env.engine.obs_shape(), env.engine.obs_dtype()), np.empty((n, A), np.float32),
+              np.empty((n, A), np.uint8), np.empty((n, A), np.uint8), np.empty((n, A), np.uint8), np.empty((n, A), np.uint8))
     for t in range(T):
-        o, rew, te, tr = env.step(torch.from_numpy(actions[t]).cuda())
+        if path == "device":
+            o, rew, te, tr = env.step(torch.from_numpy(actions[t]).cuda())
+            o, rew, te, tr = o.cpu().numpy(), rew.cpu().numpy(), te.cpu().numpy(), tr.cpu().numpy()
+        else:
+            env.engine.step_host(actions[t], hb[0], hb[1], hb[2], hb[3], active=hb[4], was_on_goal=hb[5])
+            o, rew, te, tr = hb[0], hb[1], hb[2].astype(bool), hb[3].astype(bool)
         out = co.run(actions[t:t + 1], auto_reset=auto_reset)
         assert np.array_equal(env.get_agents_xy().cpu().numpy() + r, co.pos), (gc, t)
         assert np.array_equal(env.get_targets_xy().cpu().numpy() + r, co.tgt), (gc, t)
         assert np.array_equal(env.is_active.cpu().numpy().astype(np.uint8), co.active), (gc, t)
-        og = o.cpu().numpy()
+        if path != "device":
+            assert np.array_equal(hb[4], co.active), (gc, t)
+        og = o
         if fmt == "bits":
             D = 2 * r + 1
             og = np.unpackbits(og.view(np.uint8), bitorder="little").reshape(len(seeds), A, -1)[:, :, :3 * D * D]
             og = og.reshape(len(seeds), A, 3, D, D)
         assert np.array_equal(og, out["obs"]), (gc, t)
-        assert np.array_equal(rew.cpu().numpy(), out["rewards"]), (gc, t)
-        assert np.array_equal(te.cpu().numpy(), out["terminated"]) and np.array_equal(tr.cpu().numpy(), out["truncated"])
+        assert np.array_equal(rew, out["rewards"]), (gc, t)
+        assert np.array_equal(te, out["terminated"]) and np.array_equal(tr, out["truncated"])
     env.check_errors()
     env.close()
 
@@ -67,7 +80,9 @@ def test_random_configurations(case, monkeypatch):
             pass
     if not ok_seeds:
         pytest.skip("no placeable seed")
-    run_both(gc, ok_seeds, T=24, auto_reset=bool(case % 2), team=team, fmt="bits" if case % 5 == 4 else "u8")
+    fmt = "bits" if case % 5 == 4 else "u8"
+    path = "device" if fmt == "bits" else ("device", "packed", "plain")[(case // 2) % 3]
+    run_both(gc, ok_seeds, T=24, auto_reset=bool(case % 2), team=team, fmt=fmt, path=path)
 
 
 def test_rectangular_map_and_single_agent():
