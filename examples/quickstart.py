@@ -42,3 +42,19 @@ for launch in range(4):                                                 # 64 ste
     obs_k, rew_k, term_k, trunc_k = venv.rollout(actions, obs_out=ring)
 print("rollout:", tuple(rew_k.shape), "rewards in the last 16 steps", float(rew_k.sum()))
 print("metrics of the finished episodes:", {k: float(v.mean()) for k, v in venv.metrics().items()})
+
+# 4. host buffers (numpy in, numpy out): the packed transport brings uint8 observations over PCIe as bits ----
+import numpy as np
+acts = np.random.default_rng(0).integers(0, 5, size=(4096, 64)).astype(np.uint8)
+obs_h, rew_h, term_h, trunc_h = venv.step_host(acts)                     # pgm_step_host, 'auto' = packed for big tensors
+print("host step:", obs_h.shape, obs_h.dtype, venv.engine.host_transport_info())
+
+# 5. history, undo and an SVG animation of one episode ---------------------------------------------------------
+from pogema_b200 import AnimationConfig, AnimationMonitor
+env = AnimationMonitor(pogema_v0(GridConfig(size=8, density=0.3, num_agents=4, obs_radius=5, seed=0, max_episode_steps=32)),
+                       AnimationConfig(directory="renders/", save_every_idx_episode=None))
+env.reset()
+for t in range(10):
+    env.step(env.sample_actions())
+env.env.step_back()                                                     # PersistentWrapper: device state restored
+print("history length after 10 steps and one undo:", len(env.env.get_history()[0]), "->", env.save_animation("renders/quickstart.svg"))
