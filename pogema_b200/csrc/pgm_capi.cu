@@ -622,6 +622,15 @@ void abort_expand(pgm_engine* e) {
   e->pool->finish();
 }
 
+// Once begin_expand() has woken the pool, every exit path must leave it idle again.
+struct ExpandGuard {
+  pgm_engine* e;
+  bool armed;
+  ~ExpandGuard() {
+    if (armed) abort_expand(e);
+  }
+};
+
 // Chunked copy of the device stream; the flag copy behind chunk c is stream-ordered after it, so a host
 // thread that reads flags[c] == epoch also sees the chunk.
 int enqueue_stream_copies(pgm_engine* e, cudaStream_t s) {
@@ -634,10 +643,7 @@ int enqueue_stream_copies(pgm_engine* e, cudaStream_t s) {
                           (size_t)((u1 - u0) * e->stream_unit_bytes), cudaMemcpyDeviceToHost, s);
     if (err == cudaSuccess) err = cudaMemcpyAsync(e->h_flags + c, e->d_flags + c, 4, cudaMemcpyDeviceToHost, s);
   }
-  if (err != cudaSuccess) {
-    abort_expand(e);
-    return fail(PGM_ERR_CUDA, "stream copy failed: %s", cudaGetErrorString(err));
-  }
+  if (err != cudaSuccess) return fail(PGM_ERR_CUDA, "stream copy failed: %s", cudaGetErrorString(err));
   return PGM_OK;
 }
 
@@ -1082,15 +1088,13 @@ int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_ite
   e->t_call = std::chrono::steady_clock::now();
   if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
   if (packed) begin_expand(e, obs_host);  // wake the host threads under the upload + kernel
+  ExpandGuard guard_pool{e, packed};
   CUDA_TRY(cudaMemcpyAsync(e->d_act_h, actions_host, NA * action_itemsize, cudaMemcpyHostToDevice, s));
   e->ovr_stream = packed;
   rc = pgm_step(e, e->d_act_h, action_itemsize, obs_host ? (packed ? e->d_stream : e->d_obs_h) : nullptr, e->d_rew_h,
                 e->d_term_h, e->d_trunc_h, stream);
   e->ovr_stream = false;
-  if (rc != PGM_OK) {
-    if (packed) abort_expand(e);
-    return rc;
-  }
+  if (rc != PGM_OK) return rc;
   e->last_h2d_bytes = (int64_t)(NA * action_itemsize);
   e->last_d2h_bytes = (int64_t)(NA * 6) + (obs_host ? (packed ? e->stream_bytes : e->obs_bytes) : 0) +
                       (active_host ? (int64_t)NA * 8 : 0) + (was_on_goal_host ? (int64_t)NA : 0);
@@ -1124,7 +1128,10 @@ int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_ite
       state_host = e->h_state_tmp.data();
     }
     if (was_on_goal_host) CUDA_TRY(cudaMemcpyAsync(was_on_goal_host, e->d_was, NA, cudaMemcpyDeviceToHost, s));
-    if (packed && (rc = drain_expand(e)) != PGM_OK) return rc;
+    if (packed) {
+      guard_pool.armed = false;  // drain_expand runs the job to its end itself
+      if ((rc = drain_expand(e)) != PGM_OK) return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
   }
   if (active_host)
@@ -1142,15 +1149,14 @@ int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream) {
   const bool packed = use_packed(e);
   if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
   if (packed) begin_expand(e, obs_host);
+  ExpandGuard guard_pool{e, packed};
   e->ovr_stream = packed;
   rc = pgm_observe(e, packed ? e->d_stream : e->d_obs_h, stream);
   e->ovr_stream = false;
-  if (rc != PGM_OK) {
-    if (packed) abort_expand(e);
-    return rc;
-  }
+  if (rc != PGM_OK) return rc;
   if (packed) {
     if ((rc = enqueue_stream_copies(e, s)) != PGM_OK) return rc;
+    guard_pool.armed = false;
     if ((rc = drain_expand(e)) != PGM_OK) return rc;
   } else {
     CUDA_TRY(cudaMemcpyAsync(obs_host, e->d_obs_h, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, s));

@@ -125,3 +125,25 @@ def test_step_host_ex_flags_match_state(envs, mode):
     # flags are optional, individually
     a.engine.step_host(acts[0], None, rew, te, tr, active=active)
     a.engine.step_host(acts[0], obs, rew, te, tr, was_on_goal=was)
+
+
+def test_failed_packed_call_leaves_the_pool_usable():
+    """A packed host call that fails after the widening threads were woken (step before any task exists) must
+    return an error, not hang, and the next call must work."""
+    from pogema_b200 import GridConfig
+    from pogema_b200._native import PgmError
+    from pogema_b200.engine import Engine
+    gc = GridConfig(size=8, density=0.2, num_agents=4, obs_radius=2, seed=1)
+    e = Engine(gc, 6)
+    e.set_host_transport("packed", 3)
+    obs, rew, te, tr = _host_bufs(e)
+    acts = np.zeros((6, 4), np.uint8)
+    for _ in range(2):
+        with pytest.raises(PgmError):
+            e.step_host(acts, obs, rew, te, tr)
+    e.generate(list(range(6)))
+    e.reset()
+    ref = e.observe_host()
+    e.step_host(acts, obs, rew, te, tr)           # everybody stays: the observation equals the reset one
+    assert np.array_equal(obs, ref)
+    e.close()
