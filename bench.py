@@ -370,7 +370,7 @@ def run_cuda(args):
         env.engine.step_host(h_act[i % 4].numpy(), h_obs.numpy(), h_rew.numpy(), h_term.numpy(), h_trunc.numpy(), sptr)
 
     def time_host_steps():
-        for i in range(3):
+        for i in range(8):  # first calls allocate staging buffers and start the widening threads
             host_step(i)
         barrier()
         t0 = time.perf_counter()
@@ -480,7 +480,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--instances", type=int, default=INSTANCES_PER_GPU, help="instances per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=96)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-per-launch", type=int, default=16,
