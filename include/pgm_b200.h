@@ -52,7 +52,9 @@ enum {
   PGM_OBS_U8 = 0,  /* uint8 [N][A][3][D][D], values 0/1, channels obstacles/agents/target
                       (upstream envs.py :: _get_agents_obs; float32 upstream, same values)       */
   PGM_OBS_BITS = 1,/* uint32 [N][A][ceil(3*D*D/32)], bit k = element k of the uint8 layout       */
-  PGM_OBS_F32 = 2  /* float32 [N][A][3][D][D], values 0.0/1.0 - the reference's own dtype         */
+  PGM_OBS_F32 = 2, /* float32 [N][A][3][D][D], values 0.0/1.0 - the reference's own dtype         */
+  PGM_OBS_F16 = 3  /* float16 [N][A][3][D][D], values 0.0/1.0 - for half-precision policies: the
+                      kernel writes what `obs.half()` would, without the extra pass over the tensor */
 };
 /* pgm_get_state / pgm_state_ptr selectors */
 enum {
@@ -237,7 +239,7 @@ int pgm_set_host_transport(pgm_engine* e, int32_t mode, int32_t num_threads);
  * stream idle (= return). */
 int pgm_host_transport_info(const pgm_engine* e, int64_t* out, int32_t n);
 /* The widening loop of the packed transport on its own (no CUDA call; used by the CPU tests): bit k of
- * the little-endian word stream src_host -> element k of dst_host (elem_size 1: uint8 0/1, 4: float32). */
+ * the little-endian word stream src_host -> element k of dst_host (elem_size 1: uint8 0/1, 2: float16, 4: float32 0.0/1.0). */
 int pgm_expand_bits_host(const uint32_t* src_host, int64_t nbits, void* dst_host, int32_t elem_size);
 
 /* State access (debugging, env.grid accessors, checkpoint/resume). */

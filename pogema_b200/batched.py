@@ -30,7 +30,8 @@ class BatchedPogema:
 
     ``reset() -> obs``; ``step(actions) -> obs, rewards, terminated, truncated``:
       obs         uint8  [N, A, 3, D, D]   (uint32 [N, A, ceil(3*D*D/32)] with obs_format='bits',
-                                          float32 [N, A, 3, D, D] - the reference's dtype - with obs_format='f32')
+                                          float32 [N, A, 3, D, D] - the reference's dtype - with obs_format='f32',
+                                          float16 with obs_format='f16': what obs.half() would give, without the pass)
       rewards     float32 [N, A]
       terminated  bool   [N, A]
       truncated   bool   [N, A]
@@ -87,7 +88,7 @@ class BatchedPogema:
 
     def _alloc_obs(self) -> torch.Tensor:
         e = self.engine
-        dtype = {"bits": torch.int32, "f32": torch.float32}.get(e.obs_format, torch.uint8)
+        dtype = {"bits": torch.int32, "f32": torch.float32, "f16": torch.float16}.get(e.obs_format, torch.uint8)
         return torch.empty(e.obs_shape(), dtype=dtype, device=self.device)
 
     def new_obs_buffer(self) -> torch.Tensor:
@@ -130,7 +131,7 @@ class BatchedPogema:
         truncated out (copies host<->device inside the call; page-locked result buffers are reused)."""
         if not hasattr(self, "_h_out"):
             e = self.engine
-            odt = {"bits": torch.int32, "f32": torch.float32}.get(e.obs_format, torch.uint8)
+            odt = {"bits": torch.int32, "f32": torch.float32, "f16": torch.float16}.get(e.obs_format, torch.uint8)
             n, a = self.num_envs, self.num_agents
             self._h_out = (torch.empty(e.obs_shape(), dtype=odt).pin_memory(),
                            torch.empty((n, a), dtype=torch.float32).pin_memory(),

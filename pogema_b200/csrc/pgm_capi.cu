@@ -42,6 +42,7 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int obs_elem_size(int fmt) { return fmt == PGM_OBS_F32 ? 4 : (fmt == PGM_OBS_F16 ? 2 : 1); }
 inline int pow2_floor(int v) {
   int p = 1;
   while (p * 2 <= v) p *= 2;
@@ -331,7 +332,7 @@ StepArgs make_args(pgm_engine* e) {
   a.obst_stride = e->obst_stride;
   a.bits_per_agent = e->bits_per_agent;
   a.stage_bpa = e->stage_bpa;
-  a.obs_format = c.obs_format;
+  a.obs_format = c.obs_format == PGM_OBS_F16 ? 4 : c.obs_format;  // kernel numbering: 3 is the raw stream
   a.max_steps = c.max_episode_steps;
   a.auto_reset = c.auto_reset;
   a.on_target = c.on_target;
@@ -606,7 +607,7 @@ void begin_expand(pgm_engine* e, void* obs_host) {
   j.src_batch_stride = e->stream_batch_bytes;
   j.batch_elems = g * e->bits_per_agent;
   j.unit_elems = A * e->bits_per_agent;
-  j.elem_size = e->cfg.obs_format == PGM_OBS_F32 ? 4 : 1;
+  j.elem_size = obs_elem_size(e->cfg.obs_format);
   e->epoch = e->epoch % 255u + 1u;  // 1..255, never the value the flags hold from the previous call
   j.flags = e->h_flags;
   j.flag_value = e->epoch * 0x01010101u;
@@ -715,7 +716,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
   if (cfg->collision_system < 0 || cfg->collision_system > 2) return fail(PGM_ERR_INVALID, "bad collision_system");
   if (cfg->on_target < 0 || cfg->on_target > 2) return fail(PGM_ERR_INVALID, "bad on_target");
   if (cfg->auto_reset < 0 || cfg->auto_reset > 2) return fail(PGM_ERR_INVALID, "auto_reset must be 0, 1 or 2");
-  if (cfg->obs_format < 0 || cfg->obs_format > 2) return fail(PGM_ERR_INVALID, "bad obs_format");
+  if (cfg->obs_format < 0 || cfg->obs_format > 3) return fail(PGM_ERR_INVALID, "bad obs_format");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev)
@@ -741,7 +742,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
     e->obs_inst_stride = A * (e->stage_bpa / 8);
   } else {
     e->stage_bpa = e->bits_per_agent;
-    e->obs_inst_stride = A * e->bits_per_agent * (cfg->obs_format == PGM_OBS_F32 ? 4 : 1);
+    e->obs_inst_stride = A * e->bits_per_agent * obs_elem_size(cfg->obs_format);
   }
   e->obs_bytes = N * e->obs_inst_stride;
   e->cells_stride = (int64_t)cfg->height * cfg->width;
@@ -1057,7 +1058,8 @@ int pgm_host_transport_info(const pgm_engine* e, int64_t* out, int32_t n) {
 
 int pgm_expand_bits_host(const uint32_t* src_host, int64_t nbits, void* dst_host, int32_t elem_size) {
   if (!src_host || !dst_host || nbits < 0) return fail(PGM_ERR_INVALID, "bad argument");
-  if (elem_size != 1 && elem_size != 4) return fail(PGM_ERR_INVALID, "elem_size must be 1 (uint8) or 4 (float32)");
+  if (elem_size != 1 && elem_size != 2 && elem_size != 4)
+    return fail(PGM_ERR_INVALID, "elem_size must be 1 (uint8), 2 (float16) or 4 (float32)");
   // the vector paths may read up to 16 bytes past the last stream word: go through a padded copy
   std::vector<uint32_t> tmp((size_t)((nbits + 31) / 32) + 8, 0u);
   memcpy(tmp.data(), src_host, (size_t)((nbits + 31) / 32) * 4);

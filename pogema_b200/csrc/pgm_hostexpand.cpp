@@ -48,6 +48,10 @@ void expand_f32_scalar(const uint8_t* src, size_t nbits, float* dst) {
   for (size_t pos = 0; pos < nbits; ++pos) dst[pos] = ((src[pos >> 3] >> (pos & 7)) & 1) ? 1.0f : 0.0f;
 }
 
+void expand_f16_scalar(const uint8_t* src, size_t nbits, uint16_t* dst) {
+  for (size_t pos = 0; pos < nbits; ++pos) dst[pos] = ((src[pos >> 3] >> (pos & 7)) & 1) ? 0x3C00 : 0;
+}
+
 // ----------------------------------------------------------------------------- AVX-512
 __attribute__((target("avx512f,avx512bw"))) void expand_u8_avx512(const uint8_t* src, size_t nbits, uint8_t* dst) {
   const __m512i one = _mm512_set1_epi8(1);
@@ -83,7 +87,37 @@ __attribute__((target("avx512f,avx512bw"))) void expand_f32_avx512(const uint8_t
   }
 }
 
+__attribute__((target("avx512f,avx512bw"))) void expand_f16_avx512(const uint8_t* src, size_t nbits, uint16_t* dst) {
+  const __m512i one = _mm512_set1_epi16(0x3C00);  // 1.0 in binary16
+  size_t pos = std::min(nbits, (size_t)(((64 - ((uintptr_t)dst & 63)) & 63) >> 1));
+  if (pos) {
+    const __mmask32 k = (__mmask32)lowmask(pos);
+    _mm512_mask_storeu_epi16(dst, k, _mm512_maskz_mov_epi16((__mmask32)get64(src, 0) & k, one));
+  }
+  for (; pos + 64 <= nbits; pos += 64) {
+    const uint64_t m = get64(src, pos);
+    _mm512_stream_si512((__m512i*)(dst + pos), _mm512_maskz_mov_epi16((__mmask32)m, one));
+    _mm512_stream_si512((__m512i*)(dst + pos + 32), _mm512_maskz_mov_epi16((__mmask32)(m >> 32), one));
+  }
+  for (; pos < nbits; pos += 32) {
+    const __mmask32 k = (__mmask32)lowmask(std::min<size_t>(32, nbits - pos));
+    _mm512_mask_storeu_epi16(dst + pos, k, _mm512_maskz_mov_epi16((__mmask32)get64(src, pos) & k, one));
+  }
+}
+
 // ----------------------------------------------------------------------------- AVX2
+__attribute__((target("avx2"))) void expand_f16_avx2(const uint8_t* src, size_t nbits, uint16_t* dst) {
+  size_t pos = std::min(nbits, (size_t)(((32 - ((uintptr_t)dst & 31)) & 31) >> 1));
+  for (size_t i = 0; i < pos; ++i) dst[i] = ((src[i >> 3] >> (i & 7)) & 1) ? 0x3C00 : 0;
+  const __m256i bit = _mm256_setr_epi16(1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, (short)0x8000);
+  const __m256i one = _mm256_set1_epi16(0x3C00);
+  for (; pos + 16 <= nbits; pos += 16) {
+    const __m256i v = _mm256_set1_epi16((short)(get64(src, pos) & 0xFFFF));
+    const __m256i hit = _mm256_cmpeq_epi16(_mm256_and_si256(v, bit), bit);
+    _mm256_stream_si256((__m256i*)(dst + pos), _mm256_and_si256(hit, one));
+  }
+  for (; pos < nbits; ++pos) dst[pos] = ((src[pos >> 3] >> (pos & 7)) & 1) ? 0x3C00 : 0;
+}
 __attribute__((target("avx2"))) void expand_u8_avx2(const uint8_t* src, size_t nbits, uint8_t* dst) {
   size_t pos = std::min(nbits, (size_t)((32 - ((uintptr_t)dst & 31)) & 31));
   for (size_t i = 0; i < pos; ++i) dst[i] = (src[i >> 3] >> (i & 7)) & 1;
@@ -136,6 +170,11 @@ void expand_bits(const uint32_t* src32, size_t nbits, void* dst, int elem_size) 
     if (k == 2) expand_u8_avx512(src, nbits, (uint8_t*)dst);
     else if (k == 1) expand_u8_avx2(src, nbits, (uint8_t*)dst);
     else expand_u8_scalar(src, nbits, (uint8_t*)dst);
+  } else if (elem_size == 2) {
+    if (((uintptr_t)dst & 1) != 0) expand_f16_scalar(src, nbits, (uint16_t*)dst);
+    else if (k == 2) expand_f16_avx512(src, nbits, (uint16_t*)dst);
+    else if (k == 1) expand_f16_avx2(src, nbits, (uint16_t*)dst);
+    else expand_f16_scalar(src, nbits, (uint16_t*)dst);
   } else {
     if (((uintptr_t)dst & 3) != 0) expand_f32_scalar(src, nbits, (float*)dst);
     else if (k == 2) expand_f32_avx512(src, nbits, (float*)dst);

@@ -11,7 +11,7 @@
 namespace pgm {
 
 // One contiguous run of the stream: bit k of `src` (little endian 32-bit words) -> element k of `dst`.
-// elem_size 1: uint8 0/1; 4: float32 0.0/1.0.  `src` may be over-read by up to 16 bytes.
+// elem_size 1: uint8 0/1; 2: float16, 4: float32 0.0/1.0.  `src` may be over-read by up to 16 bytes.
 void expand_bits(const uint32_t* src, size_t nbits, void* dst, int elem_size);
 const char* expand_isa();  // "avx512bw" | "avx2" | "scalar"
 

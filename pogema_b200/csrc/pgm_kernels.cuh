@@ -46,7 +46,7 @@ struct StepArgs {
   int obst_stride;      // uint32 words per instance (multiple of 4, >= PH*WPR + 1)
   int bits_per_agent;   // 3*D*D
   int stage_bpa;        // stage bits per agent: bits_per_agent (U8) or rounded up to 32 (BITS)
-  int obs_format;       // 0 u8, 1 bits, 2 float32, 3 raw stream (packed host transport: the stage bit stream of
+  int obs_format;       // 0 u8, 1 bits, 2 float32, 4 float16, 3 raw stream (packed host transport: the stage bit stream of
                         // every observation batch as it is; a batch starts where its first agent's words
                         // would start in format 1)
   int max_steps, auto_reset;
@@ -415,7 +415,7 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* 
         const int bb = b < head ? b : tail0 + (b - head);
         out[bb] = ((stage[bb >> 5] >> (bb & 31)) & 1u) ? 1.0f : 0.0f;
       }
-    } else {
+    } else if (p.obs_format != 4) {
       uint8_t* out = obs + (long long)n * p.obs_inst_stride + (long long)g0 * bpa;
       const int nbytes = gcount * bpa;
       int head = (int)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
@@ -452,6 +452,30 @@ __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* 
       for (int b = tid; b < head + (nbytes - tail0); b += TEAM) {
         const int bb = b < head ? b : tail0 + (b - head);
         out[bb] = (uint8_t)((stage[bb >> 5] >> (bb & 31)) & 1u);
+      }
+    } else {
+      // float16 0.0 / 1.0 for half-precision policies (no cast pass over the tensor): 8 stream bits -> 8 halves
+      uint16_t* out = reinterpret_cast<uint16_t*>(obs + (long long)n * p.obs_inst_stride) + (long long)g0 * bpa;
+      const int nel = gcount * bpa;
+      int head = (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u) >> 1);
+      head = min(head, nel);
+      const int chunks = (nel - head) >> 3;
+      uint4* out16 = reinterpret_cast<uint4*>(out + head);
+      for (int c = tid; c < chunks; c += TEAM) {
+        const uint32_t bit = (uint32_t)head + ((uint32_t)c << 3);
+        const uint32_t w = bit >> 5, sh = bit & 31u;
+        const uint32_t v = __funnelshift_r(stage[w], stage[w + 1], sh);
+        uint4 o;  // two bits -> bits 0 and 16, times 0x3C00 (= 1.0 in binary16) in both halves
+        o.x = ((v & 1u) | ((v & 2u) << 15)) * 0x3C00u;
+        o.y = (((v >> 2) & 1u) | ((v & 8u) << 13)) * 0x3C00u;
+        o.z = (((v >> 4) & 1u) | ((v & 32u) << 11)) * 0x3C00u;
+        o.w = (((v >> 6) & 1u) | ((v & 128u) << 9)) * 0x3C00u;
+        __stcs(out16 + c, o);
+      }
+      const int tail0 = head + (chunks << 3);
+      for (int b = tid; b < head + (nel - tail0); b += TEAM) {
+        const int bb = b < head ? b : tail0 + (b - head);
+        out[bb] = ((stage[bb >> 5] >> (bb & 31)) & 1u) ? (uint16_t)0x3C00u : (uint16_t)0u;
       }
     }
     if (g0 + p.batch_agents < p.A) team_sync<TEAM>(bar_id);

@@ -133,7 +133,7 @@ class Engine:
         return (self.num_envs, self.num_agents, 3, self.D, self.D)
 
     def obs_dtype(self):
-        return {"bits": np.uint32, "f32": np.float32}.get(self.obs_format, np.uint8)
+        return {"bits": np.uint32, "f32": np.float32, "f16": np.float16}.get(self.obs_format, np.uint8)
 
     def step_host(self, actions: np.ndarray, obs: Optional[np.ndarray], rewards: np.ndarray,
                   terminated: np.ndarray, truncated: np.ndarray, stream: int = 0,

@@ -90,22 +90,29 @@ def test_bits_format_equals_u8():
             ob = b.step(act)[0]
 
 
-def test_f32_format_equals_u8():
+@pytest.mark.parametrize("fmt", ["f32", "f16"])
+def test_float_formats_equal_u8(fmt):
+    """obs_format f32 (the reference's dtype) / f16 (half-precision policies): exactly u8.float() / u8.half(),
+    for single steps, multi-step launches and odd alignments (r=2: 75 elements per agent)."""
     import torch
     from pogema_b200 import BatchedPogema, GridConfig
-    for r, agents in ((2, 7), (5, 20), (9, 5)):
+    dt = {"f32": torch.float32, "f16": torch.float16}[fmt]
+    for r, agents in ((2, 7), (5, 20), (9, 5), (5, 64)):
         gc = GridConfig(size=16, density=0.3, num_agents=agents, obs_radius=r, max_episode_steps=16,
                         collision_system="priority", on_target="finish", seed=2)
         a = BatchedPogema(gc, num_envs=5, auto_reset=True)
-        b = BatchedPogema(gc, num_envs=5, auto_reset=True, obs_format="f32")
+        b = BatchedPogema(gc, num_envs=5, auto_reset=True, obs_format=fmt)
         oa, ob = a.reset(), b.reset()
-        assert ob.dtype == torch.float32 and ob.shape == oa.shape
+        assert ob.dtype == dt and ob.shape == oa.shape
         g = torch.Generator(device="cuda").manual_seed(0)
         for t in range(30):
-            assert torch.equal(ob, oa.float())
+            assert torch.equal(ob, oa.to(dt))
             act = a.sample_actions(g)
             oa = a.step(act)[0]
             ob = b.step(act)[0]
+        acts = torch.stack([a.sample_actions(g) for _ in range(6)])
+        ra, rb = a.rollout(acts), b.rollout(acts)
+        assert torch.equal(rb[0], ra[0].to(dt)) and torch.equal(ra[1], rb[1])
 
 
 def test_checkpoint_resume_and_host_step():

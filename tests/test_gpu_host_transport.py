@@ -14,7 +14,7 @@ def _host_bufs(e):
     n, a = e.num_envs, e.num_agents
     # +3: a deliberately misaligned destination (the caller owns the buffer; any alignment must work)
     raw = np.zeros(int(np.prod(e.obs_shape())) * np.dtype(e.obs_dtype()).itemsize + 64, np.uint8)
-    off = 4 if e.obs_format == "f32" else 3
+    off = {"f32": 4, "f16": 2}.get(e.obs_format, 3)
     obs = raw[off:off + raw.size - 64].view(e.obs_dtype()).reshape(e.obs_shape())
     return obs, np.empty((n, a), np.float32), np.empty((n, a), np.uint8), np.empty((n, a), np.uint8)
 
@@ -26,6 +26,8 @@ CASES = [
     (32, 64, 5, 64, "priority", "finish", "u8", True, 0),        # configs[1] shape
     (32, 64, 5, 33, "block_both", "nothing", "f32", True, 2),
     (10, 5, 2, 4, "priority", "finish", "f32", False, 1),
+    (32, 64, 5, 48, "soft", "finish", "f16", True, 0),
+    (9, 5, 3, 6, "priority", "restart", "f16", True, 2),
     (24, 40, 60, 3, "priority", "finish", "u8", True, 4),        # r=60: several observation batches per instance
     (12, 9, 4, 11, "soft", "finish", "u8", "reseed", 0),         # rebuilt tasks: masked observe pass writes the stream
 ]

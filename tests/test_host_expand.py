@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def check_all():
     lib = nat.load()
     rng = np.random.default_rng(0)
-    for es, dt in ((1, np.uint8), (4, np.float32)):
+    for es, dt in ((1, np.uint8), (2, np.float16), (4, np.float32)):
         for nbits in (0, 1, 7, 31, 32, 63, 64, 65, 127, 363, 1000, 3 * 11 * 11 * 64, 100003):
             for off in (0, 1, 3, 17, 63):
                 words = rng.integers(0, 2 ** 32, size=(nbits + 31) // 32 + 1, dtype=np.uint32)
@@ -28,7 +28,7 @@ def check_all():
                 assert (buf[:off] == 7).all() and (buf[off + nbits:] == 7).all(), (es, nbits, off)
     assert lib.pgm_expand_bits_host(None, 8, None, 1) == nat.PGM_ERR_INVALID
     w = np.zeros(1, np.uint32)
-    assert lib.pgm_expand_bits_host(w.ctypes.data, 8, w.ctypes.data, 2) == nat.PGM_ERR_INVALID
+    assert lib.pgm_expand_bits_host(w.ctypes.data, 8, w.ctypes.data, 3) == nat.PGM_ERR_INVALID
 
 
 def test_expand_native_isa():

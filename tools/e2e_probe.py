@@ -22,7 +22,7 @@ e.set_host_transport(a.mode, a.threads)
 N, A = a.n, a.agents
 pin = (lambda t: t) if a.pageable else (lambda t: t.pin_memory())
 h_act = [pin(torch.randint(0, 5, (N, A), dtype=torch.uint8)) for _ in range(4)]
-h_obs = pin(torch.empty(e.obs_shape(), dtype=torch.float32 if a.fmt == "f32" else torch.uint8))
+h_obs = pin(torch.empty(e.obs_shape(), dtype={"f32": torch.float32, "f16": torch.float16}.get(a.fmt, torch.uint8)))
 h_rew = pin(torch.empty((N, A), dtype=torch.float32)); h_te = pin(torch.empty((N, A), dtype=torch.uint8)); h_tr = pin(torch.empty((N, A), dtype=torch.uint8))
 tl = []
 for i in range(5):

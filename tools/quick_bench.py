@@ -72,7 +72,7 @@ ms = e0.elapsed_time(e1) / a.steps
 env.check_errors()
 D = 2 * a.r + 1
 P = a.size + 2 * a.r
-bytes_per = (3 * D * D if a.fmt == "u8" else 4 * ((3 * D * D + 31) // 32)) + 21 + ((P * P + 7) // 8) / a.agents
+bytes_per = ({"u8": 3 * D * D, "f16": 6 * D * D, "f32": 12 * D * D}.get(a.fmt, 4 * ((3 * D * D + 31) // 32))) + 21 + ((P * P + 7) // 8) / a.agents
 if a.noobs:
     bytes_per = 21 + ((P * P + 7) // 8) / a.agents
 rate = a.n * a.agents / (ms * 1e-3)
