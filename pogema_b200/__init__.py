@@ -21,10 +21,11 @@ def __getattr__(name):
     if name == "Engine":
         from .engine import Engine
         return Engine
-    if name in ("pogema_v0", "make_pogema", "Pogema", "PogemaLifeLong", "PogemaCoopFinish"):
+    if name in ("pogema_v0", "make_pogema", "make_single_agent_gym", "Pogema", "PogemaLifeLong", "PogemaCoopFinish"):
         from . import envs
         return getattr(envs, name)
-    if name in ("AnimationMonitor", "AnimationConfig", "PersistentWrapper", "AgentState", "AutoResetWrapper"):
+    if name in ("AnimationMonitor", "AnimationConfig", "PersistentWrapper", "AgentState", "AutoResetWrapper",
+                "SingleAgentWrapper", "IsMultiAgentWrapper", "MetricsForwardingWrapper"):
         from . import wrappers
         return getattr(wrappers, name)
     if name == "parallel_env":

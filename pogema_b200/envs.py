@@ -355,11 +355,29 @@ def make_pogema(grid_config=None, *args, **kwargs):
         grid_config = GridConfig(**grid_config)
     if grid_config.integration in (None, 'gymnasium'):
         return _make_pogema(grid_config)
+    if grid_config.integration == 'SampleFactory':
+        # upstream integrations/sample_factory.py wrapper stack (plain Python, needs nothing from Sample Factory)
+        from .wrappers import AutoResetWrapper, IsMultiAgentWrapper, MetricsForwardingWrapper
+        inner_cfg = grid_config.model_copy(update=dict(auto_reset=False))
+        env = IsMultiAgentWrapper(MetricsForwardingWrapper(_make_pogema(inner_cfg)))
+        if grid_config.auto_reset is None or grid_config.auto_reset:
+            env = AutoResetWrapper(env)
+        return env
     if grid_config.integration == 'PettingZoo':
         from .integrations.pettingzoo import parallel_env
         return parallel_env(grid_config)
     raise KeyError(f"integration {grid_config.integration!r} is out of scope of this engine "
-                   "(SampleFactory / PyMARL / rllib adapters wrap third-party libraries)")
+                   "(the PyMARL / rllib adapters subclass third-party base classes)")
 
 
 pogema_v0 = make_pogema
+
+
+def make_single_agent_gym(grid_config=None, *args, **kwargs):
+    """upstream integrations/make_pogema.py :: make_single_agent_gym"""
+    from .wrappers import SingleAgentWrapper
+    if grid_config is None:
+        grid_config = GridConfig(**kwargs)
+    elif isinstance(grid_config, dict):
+        grid_config = GridConfig(**grid_config)
+    return SingleAgentWrapper(_make_pogema(grid_config))

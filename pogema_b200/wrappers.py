@@ -325,3 +325,45 @@ class AutoResetWrapper(_Wrapper):
         if all(terminated) or all(truncated):
             obs, _ = self.env.reset()
         return obs, rewards, terminated, truncated, infos
+
+
+class SingleAgentWrapper(_Wrapper):
+    """upstream integrations/make_pogema.py :: SingleAgentWrapper: a single-agent gymnasium view of agent 0; the
+    other agents (if any) act at random from the env's action space."""
+
+    def step(self, action):
+        inner = self.unwrapped
+        others = [inner.action_space.sample() for _ in range(inner.get_num_agents() - 1)]
+        observations, rewards, terminated, truncated, infos = self.env.step([action] + others)
+        return observations[0], rewards[0], terminated[0], truncated[0], infos[0]
+
+    def reset(self, seed=None, return_info=True, options=None):
+        observations, infos = self.env.reset(seed=seed, options=options)
+        if return_info:
+            return observations[0], infos[0]
+        return observations[0]
+
+
+class IsMultiAgentWrapper(_Wrapper):
+    """upstream integrations/sample_factory.py :: IsMultiAgentWrapper"""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.is_multiagent = True
+
+    @property
+    def num_agents(self):
+        return self.unwrapped.get_num_agents()
+
+
+class MetricsForwardingWrapper(_Wrapper):
+    """upstream integrations/sample_factory.py :: MetricsForwardingWrapper: episode metrics are copied to
+    ``info['episode_extra_stats']`` where Sample Factory collects them."""
+
+    def step(self, action):
+        from copy import deepcopy
+        observations, rewards, terminated, truncated, infos = self.env.step(action)
+        for info in infos:
+            if 'metrics' in info:
+                info.update(episode_extra_stats=deepcopy(info['metrics']))
+        return observations, rewards, terminated, truncated, infos

@@ -104,3 +104,49 @@ def test_auto_reset_wrapper_and_persistent_auto_reset():
         ob, rb, tb, trb, _ = b.step(act)
         assert np.array_equal(np.stack(oa), np.stack(ob)) and ra == rb and ta == tb and tra == trb
         assert len(b.get_history()[0]) == (t + 1) % 5 + 1
+
+
+def test_single_agent_gym_matches_oracle():
+    from pogema_b200 import GridConfig, make_single_agent_gym
+    kw = dict(size=8, density=0.2, num_agents=1, obs_radius=3, max_episode_steps=20, seed=11)
+    env = make_single_agent_gym(GridConfig(**kw))
+    ref = orc.pogema_v0(orc.GridConfig(**kw))
+    o, info = env.reset()
+    ro, rinfo = ref.reset()
+    assert o.shape == (3, 7, 7) and np.array_equal(o, ro[0]) and info == rinfo[0]
+    assert env.reset(return_info=False).shape == (3, 7, 7)
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        a = int(rng.integers(0, 5))
+        o, r, te, tr, info = env.step(a)
+        ro, rr, rte, rtr, rinfo = ref.step([a])
+        assert np.array_equal(o, ro[0]) and r == rr[0] and te == rte[0] and tr == rtr[0]
+        assert info["is_active"] == rinfo[0]["is_active"]
+        if te or tr:
+            assert info["metrics"] == rinfo[0]["metrics"]
+            break
+    multi = make_single_agent_gym(GridConfig(size=8, density=0.1, num_agents=3, obs_radius=2, seed=1))
+    o, _ = multi.reset()
+    o, r, te, tr, info = multi.step(0)               # the other two agents act at random
+    assert o.shape == (3, 5, 5) and isinstance(r, float)
+
+
+def test_sample_factory_wrapper_stack():
+    from pogema_b200 import AutoResetWrapper, GridConfig, pogema_v0
+    kw = dict(size=8, density=0.2, num_agents=3, obs_radius=2, max_episode_steps=6, seed=4)
+    env = pogema_v0(GridConfig(integration="SampleFactory", **kw))
+    assert isinstance(env, AutoResetWrapper) and env.is_multiagent and env.num_agents == 3
+    ref = orc.pogema_v0(orc.GridConfig(**kw))
+    env.reset(), ref.reset()
+    ends = 0
+    for t in range(20):
+        act = ref.sample_actions()
+        o, r, te, tr, infos = env.step(act)
+        ro, rr, rte, rtr, rinfos = ref.step(act)
+        assert r == list(rr) and te == list(rte) and tr == list(rtr)
+        if all(rte) or all(rtr):
+            ends += 1
+            assert infos[0]["episode_extra_stats"] == rinfos[0]["metrics"] == infos[0]["metrics"]
+            ro, _ = ref.reset()                      # the stack auto-resets: the observation is the reset one
+        assert np.array_equal(np.stack(o), np.stack(ro))
+    assert ends >= 3
