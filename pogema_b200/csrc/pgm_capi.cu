@@ -87,7 +87,8 @@ struct pgm_engine {
   // d_obs_h / d_rew_h / d_term_h / d_trunc_h are parts of ONE device block (d_obs_h is its base); small results
   // (single instances behind the list API) come back with one copy into pinned staging and one synchronisation
   int64_t out_block_bytes = 0, off_rew = 0, off_term = 0, off_trunc = 0;
-  uint8_t* h_small = nullptr;  // pinned: [block | state NA*8 | was NA], only if the block is <= kSmallBlock
+  uint8_t* h_small = nullptr;  // pinned: [block | state NA*8 | was NA | actions NA*8], only if the block is <= kSmallBlock
+  uint8_t* h_small_dev = nullptr;  // the same memory as the device sees it (zero-copy results of tiny engines)
   std::vector<uint2> h_state_tmp;
   // host mirrors
   std::vector<uint32_t> h_obst;
@@ -473,8 +474,14 @@ int ensure_host_scratch(pgm_engine* e, int itemsize) {
     e->d_rew_h = (float*)(e->d_obs_h + e->off_rew);
     e->d_term_h = e->d_obs_h + e->off_term;
     e->d_trunc_h = e->d_obs_h + e->off_trunc;
-    if (e->out_block_bytes <= kSmallBlock)
-      CUDA_TRY(cudaHostAlloc((void**)&e->h_small, (size_t)e->out_block_bytes + NA * 9, cudaHostAllocDefault));
+    if (e->out_block_bytes <= kSmallBlock) {
+      CUDA_TRY(cudaHostAlloc((void**)&e->h_small, (size_t)e->out_block_bytes + NA * 17, cudaHostAllocMapped));
+      CUDA_TRY(cudaHostGetDevicePointer((void**)&e->h_small_dev, e->h_small, 0));
+      if (e->out_block_bytes > 64 * 1024) e->h_small_dev = nullptr;  // beyond a few instances the copy engine is the better mover
+      if (const char* v = getenv("PGM_ZERO_COPY")) {  // tuning knob: 0 = copy engine instead of direct stores
+        if (v[0] == '0') e->h_small_dev = nullptr;
+      }
+    }
   }
   if (e->act_h_itemsize < itemsize) {
     if (e->d_act_h) cudaFree(e->d_act_h);
@@ -1091,10 +1098,22 @@ int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_ite
   if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
   if (packed) begin_expand(e, obs_host);  // wake the host threads under the upload + kernel
   ExpandGuard guard_pool{e, packed};
-  CUDA_TRY(cudaMemcpyAsync(e->d_act_h, actions_host, NA * action_itemsize, cudaMemcpyHostToDevice, s));
-  e->ovr_stream = packed;
-  rc = pgm_step(e, e->d_act_h, action_itemsize, obs_host ? (packed ? e->d_stream : e->d_obs_h) : nullptr, e->d_rew_h,
-                e->d_term_h, e->d_trunc_h, stream);
+  const bool zero_copy = small && e->h_small_dev != nullptr;
+  if (zero_copy) {
+    // a tiny engine (the list API's single instance): the kernel reads the actions from and writes its results to
+    // pinned host memory itself - no copy engine round trips, only the launch and one wait
+    uint8_t* acts = e->h_small + e->out_block_bytes + NA * 9;
+    memcpy(acts, actions_host, NA * action_itemsize);
+    uint8_t* dv = e->h_small_dev;
+    e->ovr_stream = false;
+    rc = pgm_step(e, dv + e->out_block_bytes + NA * 9, action_itemsize, obs_host ? dv : nullptr, (float*)(dv + e->off_rew),
+                  dv + e->off_term, dv + e->off_trunc, stream);
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(e->d_act_h, actions_host, NA * action_itemsize, cudaMemcpyHostToDevice, s));
+    e->ovr_stream = packed;
+    rc = pgm_step(e, e->d_act_h, action_itemsize, obs_host ? (packed ? e->d_stream : e->d_obs_h) : nullptr, e->d_rew_h,
+                  e->d_term_h, e->d_trunc_h, stream);
+  }
   e->ovr_stream = false;
   if (rc != PGM_OK) return rc;
   e->last_h2d_bytes = (int64_t)(NA * action_itemsize);
@@ -1105,7 +1124,7 @@ int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_ite
     // a single instance behind the list API: everything in three async copies into pinned staging, one wait
     // (five separate copies into pageable buffers cost ~12 us each, more than the step itself)
     uint8_t* st = e->h_small + e->out_block_bytes;
-    CUDA_TRY(cudaMemcpyAsync(e->h_small, e->d_obs_h, (size_t)e->out_block_bytes, cudaMemcpyDeviceToHost, s));
+    if (!zero_copy) CUDA_TRY(cudaMemcpyAsync(e->h_small, e->d_obs_h, (size_t)e->out_block_bytes, cudaMemcpyDeviceToHost, s));
     if (active_host) CUDA_TRY(cudaMemcpyAsync(st, e->d_state, NA * 8, cudaMemcpyDeviceToHost, s));
     if (was_on_goal_host) CUDA_TRY(cudaMemcpyAsync(st + NA * 8, e->d_was, NA, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
