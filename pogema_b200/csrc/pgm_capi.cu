@@ -556,8 +556,6 @@ DevGenArgs devgen_args(pgm_engine* e, double density, bool has_map) {
   return a;
 }
 
-// auto_reset == 2: after a step, rebuild every instance whose episode ended from its next seed
-// (compact the flags -> device generator over the list -> masked observe pass)
 // ---- packed host transport ------------------------------------------------------------------------
 // The step kernel writes each instance's observation bit stream (obs_format 3), the copy engine moves it
 // to pinned staging in chunks, and host threads widen chunk c while chunk c+1 is still on the bus.
@@ -665,6 +663,8 @@ int drain_expand(pgm_engine* e) {
   return PGM_OK;
 }
 
+// auto_reset == 2: after a step, rebuild every instance whose episode ended from its next seed
+// (compact the flags -> device generator over the list -> masked observe pass)
 int enqueue_rebuilds(pgm_engine* e, void* obs_dev, cudaStream_t s) {
   if (e->gen_density < 0.0 || e->gen_explicit)
     return fail(PGM_ERR_STATE, "auto_reset=2 needs tasks built by pgm_generate / pgm_generate_device");
