@@ -179,7 +179,7 @@ int pgm_observe(pgm_engine* e, void* obs_dev, void* stream);
  * terminated, finish/restart bookkeeping, time limit, observations.
  *   actions_dev:   [N][A] integers in [0,5), element size action_itemsize (1,2,4,8 bytes,
  *                  little-endian; only the low byte is read)
- *   obs_dev:       PGM_OBS_U8 / PGM_OBS_BITS tensor (may be NULL to skip observations)
+ *   obs_dev:       observation tensor in the engine's PGM_OBS_* format (may be NULL to skip observations)
  *   rewards_dev:   float32 [N][A];  terminated_dev, truncated_dev: uint8 [N][A] (0/1)
  */
 int pgm_step(pgm_engine* e, const void* actions_dev, int32_t action_itemsize, void* obs_dev,
@@ -221,11 +221,11 @@ int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_ite
 int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream);
 
 /*
- * How pgm_step_host / pgm_observe_host bring PGM_OBS_U8 / PGM_OBS_F32 observations to the host.
+ * How pgm_step_host / pgm_observe_host bring PGM_OBS_U8 / PGM_OBS_F16 / PGM_OBS_F32 observations to the host.
  *   mode 0 (plain):  the kernel writes the final tensor, the copy engine moves all of it (PCIe-bound:
- *                    3*D*D bytes, or 4x that, per agent).
+ *                    3*D*D bytes, or 2x / 4x that, per agent).
  *   mode 1 (packed): the kernel writes the observation BIT STREAM (1 bit per element, every bit still
- *                    computed on the GPU), the copy engine moves 1/8 (1/32) of the bytes in chunks into
+ *                    computed on the GPU), the copy engine moves 1/8 (1/16, 1/32) of the bytes in chunks into
  *                    pinned staging owned by the engine, and `num_threads` host threads (0 = all cores,
  *                    at most 32) widen bit k to element k of obs_host with non-temporal stores while
  *                    later chunks are still on the bus.  obs_host receives exactly the bytes of mode 0.
