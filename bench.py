@@ -7,15 +7,26 @@
 A "step" is one pass of the hot path (move/collision + on_target bookkeeping +
 time limit + observations) over every instance of the workload.
 
-Workload (BASELINE.json configs[1], the one the metric is quoted on):
+Headline workload (BASELINE.json configs[1], the one the metric is quoted on):
     4096 instances per GPU of 32x32 random maps, density 0.3, 64 agents each, obs_radius 5,
     priority collisions, on_target='finish', max_episode_steps 64, auto reset,
     uniform random actions (pre-generated, resident in HBM).
+
+The K timed steps are issued as ceil(K / 16) launches of pgm_step_many (a launch advances every
+instance by up to 16 steps and writes every step's outputs); nothing else runs in the timed region.
+The same line carries, measured after the timed region:
+    closed_loop    one launch per step (pgm_step), CUDA graph replay - what an RL loop with a policy issues
+    configs        the other BASELINE.json configurations (configs[2], [3], [4] r=3/5/7 at this world size),
+                   both launch forms, each against its own algorithmic bytes
+    e2e            pgm_step_host with HOST buffers (copies inside the timed windows)
+    sharding_check rank k's results == the C oracle / a single-GPU run of the same global seeds
+    cpu_baseline   the oracle port on the host cores (N=1 only)
 
 One JSON line on stdout (rank 0).  See the task contract for the keys.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -33,12 +44,22 @@ WORKLOAD = dict(size=32, density=0.3, num_agents=64, obs_radius=5, max_episode_s
 INSTANCES_PER_GPU = 4096
 WORKLOAD_NAME = ("configs[1]: 4096 instances/GPU of 32x32 random maps, density 0.3, 64 agents, obs_radius 5, "
                  "priority collisions, on_target=finish, max_episode_steps 64, auto-reset, random actions")
+L2_BYTES = 126e6
+STEPS_PER_LAUNCH = 16
 
 
-def algorithmic_bytes_per_agent_step(r, A, P):
+def workload_config(world, instances):
+    """The `config` object of the JSON line: the same keys and values on both arms (cuda / reference)."""
+    return {"workload": WORKLOAD_NAME, "instances_per_gpu": instances,
+            "agents_per_instance": WORKLOAD["num_agents"], "obs": "uint8 [N,A,3,11,11]",
+            "parallelism": f"instances sharded over {world} GPU(s), no collective"}
+
+
+def algorithmic_bytes_per_agent_step(r, A, PH, PW=None):
     """3(2r+1)^2 obs + 21 state/action/flags + bit-packed padded map / A."""
     D = 2 * r + 1
-    return 3 * D * D + 21 + ((P * P + 7) // 8) / A
+    PW = PH if PW is None else PW
+    return 3 * D * D + 21 + ((PH * PW + 7) // 8) / A
 
 
 # --------------------------------------------------------------------------- #
@@ -120,7 +141,7 @@ def c_oracle_throughput(cores, budget_s=4.0, n_inst=32):
 
 # --------------------------------------------------------------------------- #
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons while the GPU measurements run."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -133,7 +154,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "100"],
+                                          "-i", str(self.gpu_index), "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -166,9 +187,12 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        # median of the upper half ~ clocks under load (idle samples before/after are lower)
-        med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        # median of the upper half of the samples ~ clocks under load (idle samples before/after are lower)
+        upper = sm[len(sm) // 2:]
+        med = upper[len(upper) // 2] if upper else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons),
+                "window": "headline timed region + closed_loop + per-config measurements (the headline region alone "
+                          "is shorter than one nvidia-smi sample)"}
 
 
 def measured_peak_gbs():
@@ -197,6 +221,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
     A = WORKLOAD["num_agents"]
     # one bench "step" = one oracle step over cores*inst_per_core instances (a bounded sample of the workload),
@@ -211,7 +236,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * slowest / n_steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "sample": sample},
+        "config": workload_config(world, args.instances),
         "cpu_baseline": {"value": t_rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": t_rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -228,12 +253,81 @@ def _claim_stdout():
     return real
 
 
+def split_steps(total, per_launch):
+    """K steps as ceil(K / per_launch) launches of (nearly) equal size: 20 -> [10, 10], 8192 -> 512 x [16]."""
+    if total <= 0:
+        return []
+    n = -(-total // per_launch)
+    base, rem = divmod(total, n)
+    return [base + (1 if i < rem else 0) for i in range(n)]
+
+
+class Harness:
+    """Device-resident timing of one BatchedPogema in both launch forms."""
+
+    def __init__(self, torch, env, dev, seed, spl=STEPS_PER_LAUNCH):
+        self.torch, self.env, self.dev, self.spl = torch, env, dev, spl
+        N, A = env.num_envs, env.num_agents
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        self.n_act = 16
+        self.act_t = torch.randint(0, 5, (self.n_act, N, A), dtype=torch.uint8, device=dev, generator=gen)
+        # observation ring larger than L2 so that consecutive steps cannot hit in cache
+        self.nring = int(min(16, max(2, math.ceil(2.2 * L2_BYTES / env.engine.obs_bytes))))
+        self.ring_t = torch.stack([env.new_obs_buffer() for _ in range(self.nring)])
+        self.stream = torch.cuda.current_stream(dev)
+        self.sptr = int(self.stream.cuda_stream)
+        self.graph = None
+
+    def alloc_outputs(self, max_steps):
+        N, A, torch = self.env.num_envs, self.env.num_agents, self.torch
+        self.rew_t = torch.empty((max_steps, N, A), dtype=torch.float32, device=self.dev)
+        self.term_t = torch.empty((max_steps, N, A), dtype=torch.bool, device=self.dev)
+        self.trunc_t = torch.empty((max_steps, N, A), dtype=torch.bool, device=self.dev)
+        idx = torch.arange(max_steps, device=self.dev) % self.n_act
+        self.act_many = self.act_t[idx].contiguous()
+
+    def many(self, sizes):
+        e = self.env.engine
+        for k in sizes:
+            e.step_many(k, self.act_many.data_ptr(), 1, self.ring_t.data_ptr(), self.nring, self.rew_t.data_ptr(),
+                        self.term_t.data_ptr(), self.trunc_t.data_ptr(), self.sptr)
+
+    def single_steps(self, first, count):
+        for i in range(first, first + count):
+            self.env.step(self.act_t[i % self.n_act], out=self.ring_t[i % self.nring])
+
+    def capture_graph(self, steps=16):
+        torch = self.torch
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(self.stream)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                self.single_steps(0, steps)
+        self.stream.wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        self.graph, self.graph_steps = g, steps
+
+    def timed(self, fn):
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        fn()
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+
 def run_cuda(args):
     out = _claim_stdout()
     import numpy as np
     import torch
     import torch.distributed as dist
     from pogema_b200 import BatchedPogema, GridConfig
+    from pogema_b200 import _native as nat
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,217 +342,236 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, peak_src = measured_peak_gbs()
     N = args.instances
     A = WORKLOAD["num_agents"]
     gc = GridConfig(**WORKLOAD)
     seeds = np.arange(rank * N, (rank + 1) * N, dtype=np.uint64)  # instance k of the job <-> seed k
     env = BatchedPogema(gc, num_envs=N, device=dev, seeds=seeds, auto_reset=True)
     env.reset()
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    n_act = 16
-    acts = [torch.randint(0, 5, (N, A), dtype=torch.uint8, device=dev, generator=gen) for _ in range(n_act)]
-    # obs ring larger than L2 (4 x 95 MB > 126 MB) so consecutive steps cannot hit in cache
-    ring = [env.new_obs_buffer() for _ in range(4)]
-    stream = torch.cuda.current_stream(dev)
-
-    # The K timed steps are issued as launches of SPL consecutive steps each (pgm_step_many: one kernel
-    # advances every instance by SPL steps on its own timeline, all per-step outputs are written), plus
-    # K % SPL single-step launches.  --steps-per-launch 1 times the closed-loop form instead: one launch
-    # per step, replayed from a CUDA graph (or launched from Python with --no-graph).
     SPL = max(1, args.steps_per_launch)
-    GRAPH_STEPS = n_act
-    ring_t = torch.stack(ring)                      # [4, N, A, 3, D, D] observation ring, 4 x 95 MB > L2
-    ring = [ring_t[i] for i in range(4)]
-    act_t = torch.stack(acts)                       # [16, N, A]
-    rew_t = torch.empty((SPL, N, A), dtype=torch.float32, device=dev)
-    term_t = torch.empty((SPL, N, A), dtype=torch.bool, device=dev)
-    trunc_t = torch.empty((SPL, N, A), dtype=torch.bool, device=dev)
-    act_many = act_t[torch.arange(SPL, device=dev) % n_act].contiguous() if SPL > 1 else None
-    sptr = int(stream.cuda_stream)
+    h = Harness(torch, env, dev, 1234 + rank, SPL)
+    sizes = split_steps(args.steps, SPL) if SPL > 1 else []
+    h.alloc_outputs(max(sizes + [SPL, 1]))
 
-    def plain_steps(first, count):
-        for i in range(first, first + count):
-            env.step(acts[i % n_act], out=ring[i % 4])
-
-    def many_steps(launches):
-        for _ in range(launches):
-            env.engine.step_many(SPL, act_many.data_ptr(), 1, ring_t.data_ptr(), 4, rew_t.data_ptr(),
-                                 term_t.data_ptr(), trunc_t.data_ptr(), sptr)
-
-    plain_steps(0, max(args.warmup, 3))
-    graph = None
+    # ---- headline: EXACTLY args.steps steps, device resident -------------------------------------------
+    warm = max(args.warmup, 3)
     if SPL > 1:
-        many_steps(2)
-    elif not args.no_graph:
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(stream)
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(graph, stream=side):
-                plain_steps(0, GRAPH_STEPS)
-        stream.wait_stream(side)
-        graph.replay()  # untimed warm-up of the instantiated graph
+        h.many(split_steps(warm, SPL))          # W untimed warm-up steps, same launch form as the timed ones
+        h.many(sizes[:1])
+    else:
+        h.single_steps(0, warm)
+        if not args.no_graph:
+            h.capture_graph(16)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.25)
     barrier()
     launches0 = env.engine.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
     if SPL > 1:
-        many_steps(args.steps // SPL)
-        plain_steps(0, args.steps % SPL)
-    elif graph is not None:
-        for _ in range(args.steps // GRAPH_STEPS):
-            graph.replay()
-        plain_steps(0, args.steps % GRAPH_STEPS)
+        ms_total = h.timed(lambda: h.many(sizes))
+        launches = env.engine.launch_count - launches0
+    elif h.graph is not None:
+        reps, rem = divmod(args.steps, h.graph_steps)
+
+        def replay():
+            for _ in range(reps):
+                h.graph.replay()
+            h.single_steps(0, rem)
+        ms_total = h.timed(replay)
+        launches = reps * h.graph_steps + rem
     else:
-        plain_steps(0, args.steps)
-    e1.record(stream)
+        ms_total = h.timed(lambda: h.single_steps(0, args.steps))
+        launches = env.engine.launch_count - launches0
     barrier()
-    ms_total = e0.elapsed_time(e1)
-    # graph replays launch GRAPH_STEPS kernels each without passing through pgm_step
-    launches = (env.engine.launch_count - launches0) + (GRAPH_STEPS * (args.steps // GRAPH_STEPS) if graph is not None else 0)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ms_total)
     env.check_errors()
     ms_per_step = ms_total / args.steps
     value = world * N * A * args.steps / (ms_total * 1e-3)
 
-    # ---- closed-loop form for comparison: one kernel launch per step (what an RL loop with a policy in
-    # between would issue), replayed from a CUDA graph
+    # ---- both launch forms of one environment, a fixed amount of work each (independent of --steps) -------
+    def measure_forms(hh, n_inst, n_agents, bpa, target_ms=30.0):
+        est_us = max(2.0, n_inst * n_agents * bpa / 5.0e12 * 1e6)          # at ~5 TB/s
+        reps = int(min(128, max(3, target_ms * 1e3 / (est_us * 16))))
+        hh.alloc_outputs(16)
+        hh.many([16, 16])
+        torch.cuda.synchronize()
+        barrier()
+        ms_many = max_over_ranks(hh.timed(lambda: hh.many([16] * reps))) / (reps * 16)
+        rec = {"steps_per_launch_16": {"us_per_step": ms_many * 1e3, "agent_steps_per_s": world * n_inst * n_agents / (ms_many * 1e-3),
+                                       "roofline_frac": n_inst * n_agents * bpa / (ms_many * 1e-3) / 1e9 / peak,
+                                       "steps": reps * 16}}
+        if not args.no_graph:
+            hh.capture_graph(16)
+            barrier()
+
+            def replay():
+                for _ in range(reps):
+                    hh.graph.replay()
+            ms_cl = max_over_ranks(hh.timed(replay)) / (reps * 16)
+            rec["one_launch_per_step"] = {"us_per_step": ms_cl * 1e3, "agent_steps_per_s": world * n_inst * n_agents / (ms_cl * 1e-3),
+                                          "roofline_frac": n_inst * n_agents * bpa / (ms_cl * 1e-3) / 1e9 / peak,
+                                          "steps": reps * 16, "launch": "pgm_step, CUDA graph of 16 launches replayed"}
+        return rec
+
+    r = WORKLOAD["obs_radius"]
+    P = WORKLOAD["size"] + 2 * r
+    bpa = algorithmic_bytes_per_agent_step(r, A, P)
+    forms = measure_forms(h, N, A, bpa)
     closed_loop = None
-    if world == 1 and SPL > 1 and not args.no_graph:
-        torch.cuda.synchronize()
-        g2 = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(stream)
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(g2, stream=side):
-                plain_steps(0, GRAPH_STEPS)
-        stream.wait_stream(side)
-        g2.replay()
-        torch.cuda.synchronize()
-        reps = max(1, min(args.steps, 2048) // GRAPH_STEPS)
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(stream)
-        for _ in range(reps):
-            g2.replay()
-        c1.record(stream)
-        torch.cuda.synchronize()
-        cl_ms = c0.elapsed_time(c1) / (reps * GRAPH_STEPS)
-        closed_loop = {"value": N * A / (cl_ms * 1e-3), "unit": UNIT, "ms_per_step": cl_ms, "steps": reps * GRAPH_STEPS,
-                       "launch": "one kernel launch per step (pgm_step), CUDA graph of %d launches replayed" % GRAPH_STEPS}
+    if "one_launch_per_step" in forms:
+        cl = forms["one_launch_per_step"]
+        closed_loop = {"value": cl["agent_steps_per_s"], "unit": UNIT, "ms_per_step": cl["us_per_step"] * 1e-3,
+                       "steps": cl["steps"], "roofline_frac": cl["roofline_frac"],
+                       "launch": "one kernel launch per step (pgm_step), CUDA graph of 16 launches replayed"}
+    steady = forms["steps_per_launch_16"]
+    plan_main = env.engine.plan()
+
+    # ---- the other BASELINE.json configurations at this world size ------------------------------------------
+    config_records = []
+    if not args.no_configs:
+        from pogema_b200.maps import maze_map, warehouse_map
+        share = max(1, 16384 // world)
+        table = [
+            ("configs[2]: 1024 instances/GPU of 64x64 maze-like maps, 256 agents, r=5, soft collisions, on_target=restart",
+             1024, dict(map=maze_map(64, 3).tolist(), num_agents=256, obs_radius=5, collision_system="soft", on_target="restart"), "weak"),
+            ("configs[3]: 512 instances/GPU of 256x256 warehouse maps, 1024 agents, r=5, block_both, on_target=finish",
+             512, dict(map=warehouse_map(256).tolist(), num_agents=1024, obs_radius=5, collision_system="block_both", on_target="finish"), "weak"),
+        ] + [
+            (f"configs[4]: 1M agents over {world} GPU(s) = {share} instances/GPU of 32x32, 64 agents, r={rr}, priority/finish",
+             share, dict(size=32, density=0.3, num_agents=64, obs_radius=rr, collision_system="priority", on_target="finish"), "strong")
+            for rr in (3, 5, 7)
+        ]
+        for name, n_inst, kw, scaling in table:
+            gcc = GridConfig(max_episode_steps=64, **kw)
+            hh_, ww_ = gcc.map_shape()
+            rr, aa = gcc.obs_radius, gcc.num_agents
+            b = algorithmic_bytes_per_agent_step(rr, aa, hh_ + 2 * rr, ww_ + 2 * rr)
+            e2 = BatchedPogema(gcc, num_envs=n_inst, device=dev, seeds=np.arange(rank * n_inst, (rank + 1) * n_inst, dtype=np.uint64),
+                               auto_reset=True)
+            e2.reset()
+            h2 = Harness(torch, e2, dev, 99 + rank)
+            rec = {"config": name, "instances_per_gpu": n_inst, "agents_per_instance": aa, "scaling": scaling,
+                   "algorithmic_bytes_per_agent_step": b, "plan": e2.engine.plan(), "obs_ring_slots": h2.nring}
+            rec.update(measure_forms(h2, n_inst, aa, b))
+            e2.check_errors()
+            config_records.append(rec)
+            e2.close()
+            del h2, e2
+            torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the C-ABI host-buffer call (pgm_step_host), H2D actions + D2H obs/rewards/flags every step
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    per_window = max(32, args.e2e_steps // 3)
     h_act = [torch.randint(0, 5, (N, A), dtype=torch.uint8).pin_memory() for _ in range(4)]
     h_obs = torch.empty(env.engine.obs_shape(), dtype=torch.uint8).pin_memory()
     h_rew = torch.empty((N, A), dtype=torch.float32).pin_memory()
     h_term = torch.empty((N, A), dtype=torch.uint8).pin_memory()
     h_trunc = torch.empty((N, A), dtype=torch.uint8).pin_memory()
-    sptr = int(stream.cuda_stream)
+    sptr = h.sptr
 
-    def host_step(i):
-        env.engine.step_host(h_act[i % 4].numpy(), h_obs.numpy(), h_rew.numpy(), h_term.numpy(), h_trunc.numpy(), sptr)
-
-    def time_host_steps():
-        """e2e rate of the host-buffer call: three back-to-back windows of e2e_steps / 3 steps each, the median
-        window is reported (the widening threads share the host with whatever else runs on the box; all three
-        window rates are kept in the JSON line)."""
+    def time_host_steps(engine, obs_np):
+        """e2e rate of the host-buffer call: three back-to-back windows of `per_window` steps each (independent of
+        --steps), the median window is reported (the widening threads share the host with whatever else runs on
+        the box; all three window rates are kept in the JSON line)."""
+        def host_step(i):
+            engine.step_host(h_act[i % 4].numpy(), obs_np, h_rew.numpy(), h_term.numpy(), h_trunc.numpy(), sptr)
         for i in range(8):  # first calls allocate staging buffers and start the widening threads
             host_step(i)
-        per = max(1, e2e_steps // 3)
         rates = []
         for w in range(3):
             barrier()
             t0 = time.perf_counter()
-            for i in range(per):
+            for i in range(per_window):
                 host_step(i)
-            barrier()
-            dt = time.perf_counter() - t0
-            if world > 1:
-                t = torch.tensor([dt], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-            rates.append(world * N * A * per / dt)
-        info = env.engine.host_transport_info()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            rates.append(world * N * A * per_window / dt)
+        info = engine.host_transport_info()
         return {"value": sorted(rates)[1], "unit": UNIT, "h2d_bytes_per_step": info["h2d_bytes"],
-                "d2h_bytes_per_step": info["d2h_bytes"], "steps": 3 * per, "window_rates": rates}
+                "d2h_bytes_per_step": info["d2h_bytes"], "steps": 3 * per_window, "window_rates": rates}
 
     # Two transports of the same call, same uint8 result in the caller's host buffer (pgm_set_host_transport):
     # packed = the kernel writes the observation bit stream, the copy engine moves 1/8 of the bytes, host
     # threads widen it into h_obs while later chunks are on the bus; plain = DMA of the final uint8 tensor.
     host_threads = max(1, (os.cpu_count() or 1) // world)
     env.engine.set_host_transport("packed", host_threads)
-    e2e_packed = time_host_steps()
+    e2e_packed = time_host_steps(env.engine, h_obs.numpy())
     e2e_packed["api"] = ("pgm_step_host (C-ABI, host buffers), packed transport: GPU-written bit stream over PCIe, "
-                         "%d host threads (%s) widen it to uint8 [N,A,3,11,11]" % (host_threads, env.engine.host_transport_info()["isa"]))
+                         "%d host threads per rank (%s) widen it to uint8 [N,A,3,11,11]" % (host_threads, env.engine.host_transport_info()["isa"]))
     env.engine.set_host_transport("plain")
-    e2e_plain = time_host_steps()
+    e2e_plain = time_host_steps(env.engine, h_obs.numpy())
     e2e_plain["api"] = "pgm_step_host (C-ABI, pinned host buffers), plain transport: DMA of the uint8 tensor (PCIe-bound)"
     env.engine.set_host_transport("auto")
     e2e, e2e_other = (e2e_packed, e2e_plain) if e2e_packed["value"] >= e2e_plain["value"] else (e2e_plain, e2e_packed)
-    h2d = N * A
 
-    # same call with the bit-packed observation format (48 B instead of 363 B per agent over PCIe)
-    e2e_bits = None
-    if world == 1:
-        envb = BatchedPogema(gc, num_envs=N, device=dev, seeds=seeds, auto_reset=True, obs_format="bits")
-        envb.reset()
-        hb_obs = torch.empty(envb.engine.obs_shape(), dtype=torch.int32).pin_memory()
+    # The packed transport is bound by the host's DRAM: every rank's threads write obs_bytes of uint8 per step into
+    # one host.  Ceiling = a plain non-temporal fill of the same buffer by the same number of threads on every rank
+    # at the same time (pgm_host_fill_gbps); `frac_of_ceiling` = bytes/s the widening loop wrote / that.
+    barrier()
+    fill = float(nat.load().pgm_host_fill_gbps(h_obs.data_ptr(), h_obs.numel(), host_threads, 6))
+    if world > 1:
+        t = torch.tensor([fill], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        fill_total = float(t.item())
+    else:
+        fill_total = fill
+    written_gbs = e2e_packed["value"] / (N * A) * env.engine.obs_bytes / 1e9   # all ranks
+    host_dram = {"nt_fill_GBps_all_ranks": fill_total, "threads_per_rank": host_threads, "bytes": int(h_obs.numel()),
+                 "packed_transport_write_GBps_all_ranks": written_gbs, "frac_of_ceiling": written_gbs / max(fill_total, 1e-9),
+                 "how": "pgm_host_fill_gbps: every rank fills its own pinned observation buffer at the same time, "
+                        "_mm512_stream (or AVX2 / memset), 6 passes"}
 
-        def host_step_bits(i):
-            envb.engine.step_host(h_act[i % 4].numpy(), hb_obs.numpy(), h_rew.numpy(), h_term.numpy(), h_trunc.numpy(), sptr)
+    # same call with the bit-packed observation format (48 B instead of 363 B per agent over PCIe, no widening)
+    envb = BatchedPogema(gc, num_envs=N, device=dev, seeds=seeds, auto_reset=True, obs_format="bits")
+    envb.reset()
+    hb_obs = torch.empty(envb.engine.obs_shape(), dtype=torch.int32).pin_memory()
+    e2e_bits = time_host_steps(envb.engine, hb_obs.numpy())
+    e2e_bits["api"] = "pgm_step_host with obs_format=bits (uint32 [N,A,12], bit k = element k of the uint8 layout)"
+    envb.close()
 
-        for i in range(3):
-            host_step_bits(i)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            host_step_bits(i)
-        torch.cuda.synchronize()
-        tb = time.perf_counter() - t0
-        e2e_bits = {"value": N * A * e2e_steps / tb, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": envb.engine.obs_bytes + N * A * 4 + 2 * N * A, "steps": e2e_steps,
-                    "api": "pgm_step_host with obs_format=bits (uint32 [N,A,12], bit k = element k of the uint8 layout)"}
-        envb.close()
+    # ---- sharding check (untimed): rank k's instances [k*N, (k+1)*N) give what a single-GPU run of the same
+    # global seeds gives, and what the C oracle gives
+    sharding = sharding_check(torch, dist, np, BatchedPogema, gc, dev, rank, world, N, A)
 
     if rank == 0:
-        r = WORKLOAD["obs_radius"]
-        P = WORKLOAD["size"] + 2 * r
-        bpa = algorithmic_bytes_per_agent_step(r, A, P)
-        peak, peak_src = measured_peak_gbs()
-        achieved = N * A * bpa / (ms_per_step * 1e-3) / 1e9
         traffic = ncu_traffic_bytes()
+        achieved = N * A * bpa / (ms_per_step * 1e-3) / 1e9
+        cfg = workload_config(world, N)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "instances_per_gpu": N, "agents_per_instance": A,
-                       "obs": "uint8 [N,A,3,11,11]", "actions": "uint8 resident in HBM, 16 pre-generated tensors",
-                       "l2": "obs written to a ring of 4 buffers (4 x %.0f MB > 126 MB L2)" % (env.engine.obs_bytes / 1e6),
-                       "launch": ("pgm_step_many: %d steps per kernel launch (every step writes all its outputs)" % SPL) if SPL > 1
-                       else (("one launch per step, CUDA graph of %d launches replayed" % GRAPH_STEPS) if graph is not None else "one pgm_step call per step"),
-                       "steps_per_launch": SPL,
-                       "plan": env.engine.plan(), "parallelism": f"instances sharded over {world} GPU(s), no collective"},
+            "config": cfg,
+            "details": {"actions": "uint8 resident in HBM, 16 pre-generated tensors",
+                        "l2": "obs written to a ring of %d buffers (%d x %.0f MB > 126 MB L2)" % (h.nring, h.nring, env.engine.obs_bytes / 1e6),
+                        "launch": ("pgm_step_many: the %d timed steps = launches of %s steps (every step writes all its outputs)" % (args.steps, sizes if len(sizes) <= 4 else "%d x %d" % (len(sizes), sizes[0]))) if SPL > 1
+                        else (("one launch per step, CUDA graph of %d launches replayed" % h.graph_steps) if h.graph is not None else "one pgm_step call per step"),
+                        "steps_per_launch": SPL, "plan": plan_main},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000_GBps": achieved / 8000.0,
-                         "algorithmic_bytes_per_agent_step": bpa, "kernel": "pgm_step_kernel (%d step(s) per launch)" % SPL,
-                         "algorithmic_bytes_per_launch": N * A * bpa * SPL},
+                         "algorithmic_bytes_per_agent_step": bpa, "kernel": "pgm_step_kernel (pgm_step_many, up to %d steps per launch)" % SPL,
+                         "algorithmic_bytes_per_launch": N * A * bpa * (sizes[0] if sizes else 1),
+                         "steady_state": {"frac": steady["roofline_frac"], "us_per_step": steady["us_per_step"], "steps": steady["steps"],
+                                          "note": "same kernel over a longer window (16 steps per launch), for comparison with the K-step headline"}},
             "e2e": e2e,
             "e2e_other_transport": e2e_other,
             "gpu_launches": launches,
             "clocks": clocks,
             "closed_loop": closed_loop,
+            "configs": config_records,
             "e2e_bits": e2e_bits,
+            "host_dram": host_dram,
+            "sharding_check": sharding,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -480,6 +593,67 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+def sharding_check(torch, dist, np, BatchedPogema, gc, dev, rank, world, N, A, T=24, samples=3):
+    """Every rank steps its shard T times with actions that are a function of the GLOBAL instance index; rank 0
+    then (a) re-runs `samples` instances of every rank on its own GPU and (b) runs the first sample of every
+    rank on the C oracle, and compares positions, targets, active flags, reward sums and the last observation."""
+    try:
+        first = rank * N
+        env = BatchedPogema(gc, num_envs=N, device=dev, seeds=np.arange(first, first + N, dtype=np.uint64), auto_reset=True)
+        env.reset()
+
+        def actions_for(ids):
+            # [T, len(ids), A]: instance g's stream depends on g only
+            return np.stack([np.random.default_rng(77_000 + int(g)).integers(0, 5, size=(T, A)) for g in ids], axis=1).astype(np.uint8)
+
+        pick = sorted(set(int(x) for x in np.linspace(0, N - 1, samples)))
+        acts = np.zeros((T, N, A), dtype=np.uint8)
+        # all instances step (random actions), the sampled ones with their global streams
+        acts[:] = np.random.default_rng(5 + rank).integers(0, 5, size=(T, N, A))
+        acts[:, pick] = actions_for([first + k for k in pick])
+        last = torch.stack([env.new_obs_buffer()])   # one observation slot: the last step's is what is compared
+        obs, rew, term, trunc = env.rollout(torch.from_numpy(acts).to(dev), obs_out=last)
+        rsum = rew.double().sum(0)
+        mine = {"ids": [first + k for k in pick],
+                "pos": env.get_agents_xy()[pick].cpu().numpy(), "tgt": env.get_targets_xy()[pick].cpu().numpy(),
+                "active": env.is_active[pick].cpu().numpy(), "rsum": rsum[pick].cpu().numpy(),
+                "obs": obs[-1][pick].cpu().numpy()}
+        env.check_errors()
+        env.close()
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+        else:
+            parts = [mine]
+        if rank != 0:
+            return None
+        ids = [g for p in parts for g in p["ids"]]
+        ref = BatchedPogema(gc, num_envs=len(ids), device=dev, seeds=np.asarray(ids, dtype=np.uint64), auto_reset=True)
+        ref.reset()
+        robs, rrew, _, _ = ref.rollout(torch.from_numpy(actions_for(ids)).to(dev), obs_out=torch.stack([ref.new_obs_buffer()]))
+        got = {k: np.concatenate([p[k] for p in parts]) for k in ("pos", "tgt", "active", "rsum", "obs")}
+        same_gpu = (np.array_equal(got["pos"], ref.get_agents_xy().cpu().numpy())
+                    and np.array_equal(got["tgt"], ref.get_targets_xy().cpu().numpy())
+                    and np.array_equal(got["active"], ref.is_active.cpu().numpy())
+                    and np.array_equal(got["rsum"], rrew.double().sum(0).cpu().numpy())
+                    and np.array_equal(got["obs"], robs[-1].cpu().numpy()))
+        ref.close()
+        # C oracle (built from the Python oracle's reset, i.e. from numpy): the first sample of every rank
+        from oracle.c_driver import COracle
+        oid = [p["ids"][0] for p in parts]
+        co = COracle.from_python_oracle(WORKLOAD, oid)
+        o = co.run(actions_for(oid), auto_reset=True)
+        sel = [ids.index(g) for g in oid]
+        rr = WORKLOAD["obs_radius"]
+        same_oracle = (np.array_equal(got["pos"][sel] + rr, co.pos) and np.array_equal(got["tgt"][sel] + rr, co.tgt)
+                       and np.array_equal(got["active"][sel].astype(np.uint8), co.active)
+                       and np.array_equal(got["rsum"][sel], o["rewards_sum"]) and np.array_equal(got["obs"][sel], o["obs"]))
+        return {"status": "ok" if (same_gpu and same_oracle) else "MISMATCH", "steps": T, "instances_checked": ids,
+                "vs_single_gpu_rerun": bool(same_gpu), "vs_c_oracle": bool(same_oracle), "oracle_instances": oid}
+    except Exception as exc:  # the check must never take the bench line down
+        return {"status": "error", "error": repr(exc)[:300]} if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -490,8 +664,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=96)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--steps-per-launch", type=int, default=16,
-                    help="steps advanced by one kernel launch (pgm_step_many); 1 = one launch per step")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config records (configs[2..4])")
+    ap.add_argument("--steps-per-launch", type=int, default=STEPS_PER_LAUNCH,
+                    help="most steps advanced by one kernel launch (pgm_step_many); 1 = one launch per step")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graph replays")
     args = ap.parse_args()
     if args.warmup < 3:

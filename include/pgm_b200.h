@@ -241,13 +241,20 @@ int pgm_host_transport_info(const pgm_engine* e, int64_t* out, int32_t n);
 /* The widening loop of the packed transport on its own (no CUDA call; used by the CPU tests): bit k of
  * the little-endian word stream src_host -> element k of dst_host (elem_size 1: uint8 0/1, 2: float16, 4: float32 0.0/1.0). */
 int pgm_expand_bits_host(const uint32_t* src_host, int64_t nbits, void* dst_host, int32_t elem_size);
+/* Measurement aid (no CUDA call): GB/s of a plain non-temporal fill of dst_host[0..bytes) by num_threads host
+ * threads, `reps` passes - the DRAM write ceiling of this host, i.e. the bound of the packed transport's
+ * widening loop (bench.py reports it beside `e2e`).  Returns a negative value on bad arguments. */
+double pgm_host_fill_gbps(void* dst_host, int64_t bytes, int32_t num_threads, int32_t reps);
 
 /* State access (debugging, env.grid accessors, checkpoint/resume). */
 int pgm_get_state(pgm_engine* e, int32_t what, void* dst_host, int64_t dst_bytes, void* stream);
 void* pgm_state_ptr(pgm_engine* e, int32_t what); /* device pointer of the raw array, or NULL */
 
-/* Checkpoint / resume of the complete mutable state (positions, targets,
- * active flags, elapsed steps, lifelong generators, metric counters). */
+/* Checkpoint / resume of the complete mutable state: positions, targets, active flags, elapsed steps, lifelong
+ * generators, metric counters, current task seeds; with auto_reset == 2 (tasks rebuilt from new seeds every
+ * episode) also the tasks themselves (obstacle bitmaps, initial states, lifelong tables).  The blob starts with a
+ * 64-byte header (magic, ABI, shape, modes): pgm_checkpoint_load rejects a blob of another engine shape or mode
+ * and, when the tasks are not part of the blob, a blob taken from an engine built from other seeds. */
 int64_t pgm_checkpoint_bytes(const pgm_engine* e);
 int pgm_checkpoint_save(pgm_engine* e, void* dst_host, int64_t dst_bytes, void* stream);
 int pgm_checkpoint_load(pgm_engine* e, const void* src_host, int64_t src_bytes, void* stream);

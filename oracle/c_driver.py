@@ -39,6 +39,15 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _build_chunk(args):
+    gc_kwargs, seeds = args
+    co = COracle.from_python_oracle(gc_kwargs, seeds)
+    c = co.cfg
+    return dict(cfg=(c.PH, c.PW, c.A, c.r, c.collision, c.on_target, c.max_episode_steps), obstacles=co.obstacles,
+                pos=co.pos, tgt=co.tgt, rng=co.rng, comp_start=co.comp_start, comp_size=co.comp_size, cells=co.cells,
+                cells_stride=co.cells_stride)
+
+
 class COracle:
     """N instances of one config on the C oracle.  `from_python_oracle` builds the state from
     oracle.pogema_oracle resets; `from_arrays` takes explicit arrays (e.g. read back from the engine)."""
@@ -103,6 +112,28 @@ class COracle:
                         off += len(pts)
                     comp_start[n, a], comp_size[n, a] = seen[cid]
         return cls(cfg, obstacles, pos, tgt, rng, comp_start, comp_size, cells, stride)
+
+    @classmethod
+    def from_python_oracle_parallel(cls, gc_kwargs, seeds, procs=None):
+        """`from_python_oracle` for many instances: the Python oracle resets (numpy RNG, BFS, placing in pure
+        Python) run in a process pool, the per-chunk arrays are concatenated into one COracle."""
+        import multiprocessing as mp
+        seeds = [int(s) for s in seeds]
+        procs = min(procs or (os.cpu_count() or 1), max(1, len(seeds) // 8))
+        if procs <= 1:
+            return cls.from_python_oracle(gc_kwargs, seeds)
+        chunks = [seeds[i::procs] for i in range(procs)]
+        with mp.get_context("spawn").Pool(procs) as pool:
+            parts = pool.map(_build_chunk, [(gc_kwargs, c) for c in chunks])
+        order = np.argsort(np.concatenate([np.arange(len(seeds))[i::procs] for i in range(procs)]), kind="stable")
+
+        def cat(key):
+            if parts[0][key] is None:
+                return None
+            return np.ascontiguousarray(np.concatenate([p[key] for p in parts])[order])
+        cfg = OrcCfg(*parts[0]["cfg"])
+        return cls(cfg, cat("obstacles"), cat("pos"), cat("tgt"), cat("rng"), cat("comp_start"), cat("comp_size"),
+                   cat("cells"), parts[0]["cells_stride"])
 
     def run(self, actions, auto_reset=False, want_obs=True):
         """actions uint8 [T, N, A] -> dict with the outputs of the LAST step and the reward sums."""

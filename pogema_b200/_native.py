@@ -25,7 +25,7 @@ EXPORTS = [
     "pgm_obs_instance_stride", "pgm_generate", "pgm_generate_device", "pgm_generate_host", "pgm_set_tasks", "pgm_reset", "pgm_observe", "pgm_step",
     "pgm_step_many", "pgm_step_host", "pgm_step_host_ex", "pgm_observe_host", "pgm_get_state", "pgm_state_ptr", "pgm_checkpoint_bytes", "pgm_checkpoint_save",
     "pgm_checkpoint_load", "pgm_check_errors", "pgm_launch_count", "pgm_plan", "pgm_set_debug_buffer",
-    "pgm_set_host_transport", "pgm_host_transport_info", "pgm_expand_bits_host",
+    "pgm_set_host_transport", "pgm_host_transport_info", "pgm_expand_bits_host", "pgm_host_fill_gbps",
 ]
 
 
@@ -90,6 +90,8 @@ def load():
     lib.pgm_set_host_transport.argtypes = [vp, i32, i32]
     lib.pgm_host_transport_info.argtypes = [vp, C.POINTER(i64), i32]
     lib.pgm_expand_bits_host.argtypes = [vp, i64, vp, i32]
+    lib.pgm_host_fill_gbps.argtypes = [vp, i64, i32, i32]
+    lib.pgm_host_fill_gbps.restype = C.c_double
     if lib.pgm_abi_version() != PGM_ABI_VERSION:
         raise RuntimeError("libpgm_b200.so ABI version mismatch; rebuild with `make`")
     _lib = lib

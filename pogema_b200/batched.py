@@ -152,6 +152,8 @@ class BatchedPogema:
         R = K, every step's observation is kept).  Results are identical to K ``step`` calls."""
         if actions.device != self.device or actions.dim() != 3 or tuple(actions.shape[1:]) != (self.num_envs, self.num_agents):
             raise ValueError(f"actions must be a [K, {self.num_envs}, {self.num_agents}] tensor on {self.device}")
+        if actions.dtype not in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+            raise TypeError("actions must be an integer tensor")
         actions = actions.contiguous()
         K = actions.shape[0]
         with torch.cuda.device(self.device):
@@ -231,7 +233,10 @@ class BatchedPogema:
         return {"engine": self.engine.checkpoint(self._stream()), "seeds": self.seeds.copy()}
 
     def load_state_dict(self, sd: dict):
-        assert np.array_equal(sd["seeds"], self.seeds), "checkpoint belongs to different tasks"
+        """Restore a ``state_dict()``.  The engine validates the blob's header (shape, modes) and - unless the tasks
+        travel inside the blob (``auto_reset="reseed"``) - that it was taken from the same task seeds."""
+        if not np.array_equal(sd["seeds"], self.seeds):
+            raise ValueError("checkpoint belongs to different tasks (initial seeds differ)")
         self.engine.restore(sd["engine"], self._stream())
 
     def check_errors(self):

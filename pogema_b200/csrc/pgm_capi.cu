@@ -110,6 +110,8 @@ struct pgm_engine {
   int regen_slots = 0;
   int64_t launches = 0;
   bool use_pdl = true;
+  bool serialize_next = false;  // the next launch follows a kernel that rewrote d_obst (device generator): it must not
+                                // start its bulk copy of the obstacle bitmap before that kernel has completed
   // packed host transport (pgm_step_host / pgm_observe_host): device bit stream -> pinned staging -> host threads
   int host_transport = -1;      // -1 auto, 0 plain (DMA of the final tensor), 1 packed
   int host_threads = 0;         // 0 = hardware concurrency (at most 32)
@@ -125,6 +127,7 @@ struct pgm_engine {
   int64_t last_us[5] = {0, 0, 0, 0, 0};  // packed pgm_step_host: enqueue done, first chunk landed, last chunk landed, widening done, stream idle
   std::chrono::steady_clock::time_point t_call;
   int stream_chunks = 8;
+  cudaStream_t expand_stream = nullptr;  // stream of the packed host call in flight (stream_failed)
 };
 
 namespace {
@@ -300,7 +303,8 @@ int compute_plan(pgm_engine* e) {
 
 int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
   LaunchDims d{e->team, static_radius(e->cfg.obs_radius), e->grid, e->cta_threads, e->smem_cta, e->cfg.device,
-               e->use_pdl ? 1 : 0, e->occ_mode, e->obst_global};
+               (e->use_pdl && !e->serialize_next) ? 1 : 0, e->occ_mode, e->obst_global};
+  e->serialize_next = false;
   // huge maps (obstacles in global memory) only have the generic and the r=5 variants
   if (d.og && d.rt != 5) d.rt = 0;
   const int g = d.og ? (d.rt == 5 ? 1 : 0) : radius_group(d.rt);
@@ -600,8 +604,18 @@ int ensure_stream(pgm_engine* e) {
   return PGM_OK;
 }
 
-void begin_expand(pgm_engine* e, void* obs_host) {
+// Polled by the widening loop when a chunk flag is overdue: has the stream feeding the staging buffer failed?
+bool stream_failed(void* ctx) {
+  pgm_engine* e = (pgm_engine*)ctx;
+  const cudaError_t q = cudaStreamQuery(e->expand_stream);
+  return q != cudaSuccess && q != cudaErrorNotReady;
+}
+
+void begin_expand(pgm_engine* e, void* obs_host, cudaStream_t s) {
   pgm::ExpandJob j;
+  e->expand_stream = s;
+  j.producer_failed = stream_failed;
+  j.producer_ctx = e;
   const int64_t A = e->cfg.num_agents, g = e->batch_agents;
   j.src = e->h_stream;
   j.dst = (uint8_t*)obs_host;
@@ -660,6 +674,10 @@ int drain_expand(pgm_engine* e) {
   e->last_us[1] = e->pool->first_chunk_us();
   e->last_us[2] = e->pool->last_chunk_us();
   e->last_us[3] = us_since(e);
+  if (e->pool->aborted()) {
+    const cudaError_t q = cudaStreamQuery(e->expand_stream);
+    return fail(PGM_ERR_CUDA, "the stream feeding the packed host transport failed: %s", cudaGetErrorString(q));
+  }
   return PGM_OK;
 }
 
@@ -691,6 +709,10 @@ int enqueue_rebuilds(pgm_engine* e, void* obs_dev, cudaStream_t s) {
   if (err != 0) return fail(PGM_ERR_CUDA, "device generator launch failed: %s", cudaGetErrorString((cudaError_t)err));
   e->launches += 2;
   e->h_obst_valid = false;
+  // The step kernel's prologue copies the obstacle bitmap BEFORE griddepcontrol.wait; with programmatic
+  // serialization it could read d_obst while the generator grid is still writing it.  The launch that follows a
+  // rebuild is therefore an ordinary stream-ordered one.
+  e->serialize_next = true;
   if (obs_dev) {
     StepArgs o = make_args(e);
     o.obs = (uint8_t*)obs_dev;
@@ -732,9 +754,15 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
   pgm_engine* e = new pgm_engine();
   e->cfg = *cfg;
   if (const char* v = getenv("PGM_NO_PDL")) e->use_pdl = !(v[0] == '1');
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
-  e->sm_count = prop.multiProcessorCount;
+  {
+    int sms = 0;
+    const cudaError_t pe = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (pe != cudaSuccess) {
+      delete e;
+      return fail(PGM_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(pe));
+    }
+    e->sm_count = sms;
+  }
   const int r = cfg->obs_radius;
   e->D = 2 * r + 1;
   e->PH = cfg->height + 2 * r;
@@ -927,6 +955,7 @@ int pgm_generate_device(pgm_engine* e, int32_t first, int32_t count, const uint6
     int err = launch_devgen(a, s);
     if (err != 0) return fail(PGM_ERR_CUDA, "device generator launch failed: %s", cudaGetErrorString((cudaError_t)err));
     e->launches++;
+    e->serialize_next = true;
   }
   std::vector<int> failed(count);
   CUDA_TRY(cudaMemcpyAsync(failed.data(), e->d_gen_fail, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
@@ -1074,6 +1103,14 @@ int pgm_expand_bits_host(const uint32_t* src_host, int64_t nbits, void* dst_host
   return PGM_OK;
 }
 
+double pgm_host_fill_gbps(void* dst_host, int64_t bytes, int32_t num_threads, int32_t reps) {
+  if (!dst_host || bytes < 4096 || num_threads < 1 || reps < 1) {
+    fail(PGM_ERR_INVALID, "pgm_host_fill_gbps: bad argument");
+    return -1.0;
+  }
+  return pgm::host_fill_gbps(dst_host, (size_t)bytes, num_threads, reps);
+}
+
 int pgm_step_host(pgm_engine* e, const void* actions_host, int32_t action_itemsize, void* obs_host,
                   float* rewards_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream) {
   return pgm_step_host_ex(e, actions_host, action_itemsize, obs_host, rewards_host, terminated_host, truncated_host,
@@ -1096,7 +1133,7 @@ int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_ite
   const bool small = !packed && e->h_small != nullptr;
   e->t_call = std::chrono::steady_clock::now();
   if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
-  if (packed) begin_expand(e, obs_host);  // wake the host threads under the upload + kernel
+  if (packed) begin_expand(e, obs_host, s);  // wake the host threads under the upload + kernel
   ExpandGuard guard_pool{e, packed};
   const bool zero_copy = small && e->h_small_dev != nullptr;
   if (zero_copy) {
@@ -1169,7 +1206,7 @@ int pgm_observe_host(pgm_engine* e, void* obs_host, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const bool packed = use_packed(e);
   if (packed && (rc = ensure_stream(e)) != PGM_OK) return rc;
-  if (packed) begin_expand(e, obs_host);
+  if (packed) begin_expand(e, obs_host, s);
   ExpandGuard guard_pool{e, packed};
   e->ovr_stream = packed;
   rc = pgm_observe(e, packed ? e->d_stream : e->d_obs_h, stream);
@@ -1278,27 +1315,65 @@ void* pgm_state_ptr(pgm_engine* e, int32_t what) {
   }
 }
 
-int64_t pgm_checkpoint_bytes(const pgm_engine* e) {
-  if (!e) return 0;
-  const int64_t N = e->cfg.num_envs, A = e->cfg.num_agents;
-  int64_t b = N * A * (8 + 1) + N * (4 + 1 + 16 + 16);
-  if (e->lifelong) b += N * A * (int64_t)sizeof(Pcg64);
-  return b;
+namespace {
+// Checkpoint blob: a 64-byte header (magic, ABI, shape and modes - validated on load) followed by the raw arrays.
+// With auto_reset == 2 the TASKS change every episode (new seed -> new map, starts, goals, lifelong tables), so
+// they are part of the mutable state and are saved too; otherwise the tasks are the ones the engine was built
+// with and only the per-step state is saved.
+struct CkptHeader {
+  uint32_t magic;  // 'PGMC'
+  int32_t abi, num_envs, num_agents, height, width, obs_radius, collision_system, on_target, auto_reset, lifelong;
+  int32_t reserved[5];
+};
+static_assert(sizeof(CkptHeader) == 64, "checkpoint header is 64 bytes");
+constexpr uint32_t kCkptMagic = 0x434D4750u;
+
+CkptHeader ckpt_header(const pgm_engine* e) {
+  CkptHeader h{};
+  h.magic = kCkptMagic;
+  h.abi = PGM_ABI_VERSION;
+  h.num_envs = e->cfg.num_envs;
+  h.num_agents = e->cfg.num_agents;
+  h.height = e->cfg.height;
+  h.width = e->cfg.width;
+  h.obs_radius = e->cfg.obs_radius;
+  h.collision_system = e->cfg.collision_system;
+  h.on_target = e->cfg.on_target;
+  h.auto_reset = e->cfg.auto_reset;
+  h.lifelong = e->lifelong ? 1 : 0;
+  return h;
 }
 
-namespace {
 struct CkptPart {
   void* dev;
   size_t bytes;
 };
-std::vector<CkptPart> ckpt_parts(pgm_engine* e) {
+std::vector<CkptPart> ckpt_parts(const pgm_engine* e) {
   const size_t N = e->cfg.num_envs, A = e->cfg.num_agents;
-  std::vector<CkptPart> v = {{e->d_state, N * A * 8}, {e->d_was, N * A},     {e->d_elapsed, N * 4}, {e->d_done, N},
-                             {e->d_macc, N * 16},   {e->d_mlast, N * 16}};
+  std::vector<CkptPart> v = {{e->d_state, N * A * 8}, {e->d_was, N * A},   {e->d_elapsed, N * 4},  {e->d_done, N},
+                             {e->d_macc, N * 16},     {e->d_mlast, N * 16}, {e->d_cur_seeds, N * 8}};
   if (e->lifelong) v.push_back({e->d_rng, N * A * sizeof(Pcg64)});
+  if (e->cfg.auto_reset == 2) {
+    v.push_back({e->d_obst, N * (size_t)e->obst_stride * 4});
+    v.push_back({e->d_state0, N * A * 8});
+    v.push_back({e->d_regen_flag, N});
+    if (e->lifelong) {
+      v.push_back({e->d_rng0, N * A * sizeof(Pcg64)});
+      v.push_back({e->d_cstart, N * A * 4});
+      v.push_back({e->d_csize, N * A * 4});
+      v.push_back({e->d_cells, N * (size_t)e->cells_stride * 4});
+    }
+  }
   return v;
 }
 }  // namespace
+
+int64_t pgm_checkpoint_bytes(const pgm_engine* e) {
+  if (!e) return 0;
+  int64_t b = (int64_t)sizeof(CkptHeader);
+  for (auto& p : ckpt_parts(e)) b += (int64_t)p.bytes;
+  return b;
+}
 
 int pgm_checkpoint_save(pgm_engine* e, void* dst, int64_t dst_bytes, void* stream) {
   if (!e || !dst) return fail(PGM_ERR_INVALID, "null argument");
@@ -1306,6 +1381,9 @@ int pgm_checkpoint_save(pgm_engine* e, void* dst, int64_t dst_bytes, void* strea
   DeviceGuard guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* o = (uint8_t*)dst;
+  const CkptHeader h = ckpt_header(e);
+  memcpy(o, &h, sizeof(h));
+  o += sizeof(h);
   for (auto& p : ckpt_parts(e)) {
     CUDA_TRY(cudaMemcpyAsync(o, p.dev, p.bytes, cudaMemcpyDeviceToHost, s));
     o += p.bytes;
@@ -1317,14 +1395,39 @@ int pgm_checkpoint_save(pgm_engine* e, void* dst, int64_t dst_bytes, void* strea
 int pgm_checkpoint_load(pgm_engine* e, const void* src, int64_t src_bytes, void* stream) {
   if (!e || !src) return fail(PGM_ERR_INVALID, "null argument");
   if (src_bytes < pgm_checkpoint_bytes(e)) return fail(PGM_ERR_INVALID, "checkpoint buffer too small");
+  CkptHeader h;
+  memcpy(&h, src, sizeof(h));
+  const CkptHeader want = ckpt_header(e);
+  if (h.magic != kCkptMagic) return fail(PGM_ERR_INVALID, "not a pgm checkpoint (bad magic)");
+  if (memcmp(&h, &want, sizeof(h)) != 0)
+    return fail(PGM_ERR_INVALID,
+                "checkpoint belongs to another engine: abi %d, %d envs x %d agents, map %dx%d, r=%d, collision %d, "
+                "on_target %d, auto_reset %d (this engine: abi %d, %d x %d, %dx%d, r=%d, %d, %d, %d)",
+                h.abi, h.num_envs, h.num_agents, h.height, h.width, h.obs_radius, h.collision_system, h.on_target,
+                h.auto_reset, want.abi, want.num_envs, want.num_agents, want.height, want.width, want.obs_radius,
+                want.collision_system, want.on_target, want.auto_reset);
   DeviceGuard guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
-  const uint8_t* o = (const uint8_t*)src;
+  const uint8_t* o = (const uint8_t*)src + sizeof(h);
+  if (e->cfg.auto_reset != 2) {
+    // the tasks are not part of the blob: it must have been taken from an engine built from the same seeds
+    std::vector<uint64_t> cur((size_t)e->cfg.num_envs);
+    CUDA_TRY(cudaMemcpyAsync(cur.data(), e->d_cur_seeds, cur.size() * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const uint8_t* q = o;
+    for (auto& p : ckpt_parts(e)) {
+      if (p.dev == (void*)e->d_cur_seeds) break;
+      q += p.bytes;
+    }
+    if (memcmp(q, cur.data(), cur.size() * 8) != 0)
+      return fail(PGM_ERR_INVALID, "checkpoint was taken from an engine with different task seeds");
+  }
   for (auto& p : ckpt_parts(e)) {
     CUDA_TRY(cudaMemcpyAsync(p.dev, o, p.bytes, cudaMemcpyHostToDevice, s));
     o += p.bytes;
   }
   CUDA_TRY(cudaStreamSynchronize(s));
+  if (e->cfg.auto_reset == 2) e->h_obst_valid = false;  // the maps came with the checkpoint
   return PGM_OK;
 }
 

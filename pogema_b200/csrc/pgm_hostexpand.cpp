@@ -200,7 +200,7 @@ struct ExpandPool::Impl {
   int64_t grain = 1;
   alignas(64) std::atomic<int64_t> next{0};
 
-  void run_job() {
+  void run_job(bool caller = false) {
     const ExpandJob& j = job;
     int c = 0;  // chunk of the last unit claimed (claims only move forward)
     for (;;) {
@@ -211,8 +211,14 @@ struct ExpandPool::Impl {
         while (j.units * (c + 1) / j.chunks < u1) ++c;
         // chunks land in order; x86 does not reorder the data loads before this flag load
         for (int spins = 0; j.flags[c] != j.flag_value && !aborted.load(std::memory_order_relaxed); ++spins) {
-          if (spins < 4000) _mm_pause();
-          else std::this_thread::yield();
+          if (spins < 4000) {
+            _mm_pause();
+          } else {
+            // a chunk that takes this long is unusual: the calling thread asks the producer whether it is still alive
+            if (caller && j.producer_failed != nullptr && (spins & 255) == 0 && j.producer_failed(j.producer_ctx))
+              aborted.store(true, std::memory_order_relaxed);
+            std::this_thread::yield();
+          }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
         if ((c == 0 && first_flag_us.load(std::memory_order_relaxed) < 0) ||
@@ -296,10 +302,55 @@ void ExpandPool::begin(const ExpandJob& job) {
   impl_->cv_start.notify_all();
 }
 
-void ExpandPool::work() { impl_->run_job(); }
+void ExpandPool::work() { impl_->run_job(true); }
+bool ExpandPool::aborted() const { return impl_->aborted.load(std::memory_order_relaxed); }
 int64_t ExpandPool::first_chunk_us() const { return impl_->first_flag_us.load(); }
 int64_t ExpandPool::last_chunk_us() const { return impl_->last_flag_us.load(); }
 void ExpandPool::abort() { impl_->aborted.store(true, std::memory_order_relaxed); }
+
+// Plain multi-threaded non-temporal fill: the host's DRAM write ceiling for the widening loop (bench.py).
+namespace {
+__attribute__((target("avx512f"))) void fill_avx512(uint8_t* d, size_t n) {
+  const __m512i v = _mm512_set1_epi8(1);
+  for (size_t i = 0; i + 64 <= n; i += 64) _mm512_stream_si512((__m512i*)(d + i), v);
+}
+__attribute__((target("avx2"))) void fill_avx2(uint8_t* d, size_t n) {
+  const __m256i v = _mm256_set1_epi8(1);
+  for (size_t i = 0; i + 32 <= n; i += 32) _mm256_stream_si256((__m256i*)(d + i), v);
+}
+}  // namespace
+
+double host_fill_gbps(void* dst, size_t bytes, int threads, int reps) {
+  threads = std::max(1, threads);
+  reps = std::max(1, reps);
+  uint8_t* base = (uint8_t*)(((uintptr_t)dst + 63) & ~(uintptr_t)63);
+  const size_t usable = (bytes - (size_t)(base - (uint8_t*)dst)) & ~(size_t)63;
+  const size_t slice = (usable / threads) & ~(size_t)63;
+  if (slice == 0) return 0.0;
+  const int k = isa();
+  std::atomic<int> ready{0};
+  std::atomic<bool> go{false};
+  auto body = [&](int t) {
+    uint8_t* d = base + (size_t)t * slice;
+    ready.fetch_add(1);
+    while (!go.load(std::memory_order_acquire)) _mm_pause();
+    for (int r = 0; r < reps; ++r) {
+      if (k == 2) fill_avx512(d, slice);
+      else if (k == 1) fill_avx2(d, slice);
+      else memset(d, 1, slice);
+    }
+    _mm_sfence();
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) th.emplace_back(body, t);
+  while (ready.load() < threads - 1) _mm_pause();
+  const auto t0 = std::chrono::steady_clock::now();
+  go.store(true, std::memory_order_release);
+  body(0);
+  for (auto& t : th) t.join();
+  const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return (double)slice * threads * reps / s / 1e9;
+}
 
 void ExpandPool::finish() {
   const auto t0 = std::chrono::steady_clock::now();

@@ -15,6 +15,10 @@ namespace pgm {
 void expand_bits(const uint32_t* src, size_t nbits, void* dst, int elem_size);
 const char* expand_isa();  // "avx512bw" | "avx2" | "scalar"
 
+// GB/s of a plain non-temporal fill of `bytes` at dst by `threads` threads, `reps` passes: the DRAM write
+// ceiling of this host for the widening loop above (reported by bench.py beside the e2e number).
+double host_fill_gbps(void* dst, size_t bytes, int threads, int reps);
+
 // Geometry of the packed stream of a whole observation tensor.
 struct ExpandJob {
   const uint8_t* src = nullptr;  // pinned staging copy of the device stream
@@ -33,6 +37,11 @@ struct ExpandJob {
   const volatile uint32_t* flags = nullptr;
   uint32_t flag_value = 0;
   int chunks = 1;
+  // Health check of the producer, polled by the CALLING thread (ExpandPool::work) while it waits for a flag:
+  // returns true if the stream that feeds the staging buffer has failed (sticky CUDA error), in which case the
+  // job is aborted instead of spinning forever on a flag that will never arrive.
+  bool (*producer_failed)(void* ctx) = nullptr;
+  void* producer_ctx = nullptr;
 };
 
 class ExpandPool {
@@ -45,6 +54,7 @@ class ExpandPool {
   void work();                       // the calling thread widens units too, until none is left to claim
   void abort();                      // stop waiting for flags (a failed launch): units are processed as they are
   void finish();                     // returns when every unit has been widened (sfence'd)
+  bool aborted() const;              // the job was cut short (abort() or a failed producer): the output is garbage
   int64_t first_chunk_us() const;    // microseconds after begin() at which chunk 0 / the last chunk was seen complete
   int64_t last_chunk_us() const;
  private:

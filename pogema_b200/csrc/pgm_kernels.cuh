@@ -160,6 +160,16 @@ __device__ __forceinline__ bool team_any(int bar_id, bool p) {
   }
 }
 
+// Action element idx of a tensor of 1/2/4/8-byte integers, read in full (a wide value such as 256 or -256 must
+// not alias to a valid move through its low byte); anything above 4 is reported by the caller's range check.
+__device__ __forceinline__ uint32_t load_action(const uint8_t* base, long long idx, int itemsize) {
+  if (itemsize == 1) return base[idx];
+  if (itemsize == 2) return reinterpret_cast<const uint16_t*>(base)[idx];
+  if (itemsize == 4) return reinterpret_cast<const uint32_t*>(base)[idx];
+  const unsigned long long v = reinterpret_cast<const unsigned long long*>(base)[idx];
+  return v > 4ull ? 5u : (uint32_t)v;
+}
+
 __device__ __forceinline__ int opposite(int a) { return a == 0 ? 0 : (((a - 1) ^ 1) + 1); }  // 1<->2, 3<->4
 __device__ __forceinline__ int move_dx(int a) { return a == 1 ? -1 : (a == 2 ? 1 : 0); }
 __device__ __forceinline__ int move_dy(int a) { return a == 3 ? -1 : (a == 4 ? 1 : 0); }
@@ -627,8 +637,8 @@ __global__ void __launch_bounds__(1024, 1)
       for (int a0 = tid; a0 < A; a0 += 2 * TEAM) {
         const int a1 = a0 + TEAM;
         const bool has1 = a1 < A;
-        uint32_t act0 = act_k[(ia + a0) * p.act_itemsize];
-        uint32_t act1 = has1 ? act_k[(ia + a1) * p.act_itemsize] : 0u;
+        uint32_t act0 = load_action(act_k, ia + a0, p.act_itemsize);
+        uint32_t act1 = has1 ? load_action(act_k, ia + a1, p.act_itemsize) : 0u;
         if (act0 > 4u || act1 > 4u) {
           atomicOr(p.err_flag, 1);
           if (act0 > 4u) act0 = 0u;

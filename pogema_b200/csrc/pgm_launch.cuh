@@ -2,6 +2,8 @@
 // translation units (pgm_inst_*.cu).  Each TU instantiates one (COLL, OP) pair for
 // every TEAM size and every compile-time radius, so the variants build in parallel.
 #pragma once
+#include <atomic>
+
 #include "pgm_kernels.cuh"
 
 namespace pgm {
@@ -14,13 +16,15 @@ struct LaunchDims {
 template <int TEAM, int COLL, int OP, int RT, int OCC, int OG = 0>
 int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   auto kern = pgm_step_kernel<TEAM, COLL, OP, RT, OCC, OG>;
-  static thread_local int configured_dev = -1;
-  static thread_local int configured_smem = -1;
-  if (configured_dev != d.device || configured_smem < d.smem) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem);
+  // The attribute is per (function, device) and process-wide: set it once per device to the hardware maximum, so
+  // engines of different shapes driven from different threads never lower each other's limit.
+  constexpr int kMaxSmem = 227 * 1024;
+  static std::atomic<unsigned long long> configured{0ull};  // bit d = done for device d (devices >= 64: every launch)
+  const unsigned long long bit = d.device < 64 ? (1ull << d.device) : 0ull;
+  if (!(configured.load(std::memory_order_acquire) & bit) || bit == 0ull) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return (int)e;
-    configured_dev = d.device;
-    configured_smem = d.smem;
+    configured.fetch_or(bit, std::memory_order_release);
   }
   // programmatic dependent launch: this grid may be scheduled while the previous kernel of
   // the stream drains; the kernel's griddepcontrol.wait orders every read of mutable state.

@@ -141,7 +141,10 @@ class Engine:
         """pgm_step_host / pgm_step_host_ex: one step with host buffers; ``active`` / ``was_on_goal`` (uint8 [N, A],
         optional) receive upstream's ``grid.is_active`` / ``env.was_on_goal`` in the same synchronisation."""
         actions = np.ascontiguousarray(actions)
-        assert actions.size == self.num_envs * self.num_agents
+        if actions.dtype.kind not in "iu" or actions.itemsize not in (1, 2, 4, 8):
+            raise TypeError(f"actions must be an integer array, got {actions.dtype}")
+        if actions.size != self.num_envs * self.num_agents:
+            raise ValueError(f"actions must hold {self.num_envs} x {self.num_agents} elements, got {actions.size}")
         nat.check(self.lib.pgm_step_host_ex(self.handle, _ptr(actions), actions.itemsize, _ptr(obs), _ptr(rewards),
                                             _ptr(terminated), _ptr(truncated), _ptr(active), _ptr(was_on_goal),
                                             C.c_void_p(stream)))

@@ -28,6 +28,20 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "configs[1]" in d["config"]["workload"]
+    # both arms print the same `config` object (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(1, bench.INSTANCES_PER_GPU)
+
+
+def test_timed_steps_are_split_into_multi_step_launches_only():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.split_steps(20, 16) == [10, 10]           # the driver's --steps 20: no single-step remainder
+    assert bench.split_steps(8192, 16) == [16] * 512
+    assert bench.split_steps(5, 16) == [5] and bench.split_steps(17, 16) == [9, 8]
+    for k in range(1, 100):
+        assert sum(bench.split_steps(k, 16)) == k and max(bench.split_steps(k, 16)) <= 16
 
 
 def test_reference_arm_other_ranks_exit_quietly():

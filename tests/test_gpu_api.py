@@ -145,6 +145,77 @@ def test_checkpoint_resume_and_host_step():
         assert np.array_equal(te.astype(bool), term.cpu().numpy()) and np.array_equal(tr.astype(bool), trunc.cpu().numpy())
 
 
+@pytest.mark.parametrize("ot", ["finish", "restart"])
+def test_checkpoint_with_reseeding_auto_reset_carries_the_tasks(ot):
+    """auto_reset='reseed' rebuilds maps / tasks / lifelong tables every episode: a checkpoint must restore them too
+    (into the same env after further reseeds, and into a fresh env built from the initial seeds)."""
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    gc = GridConfig(size=12, density=0.3, num_agents=9, obs_radius=3, max_episode_steps=6,
+                    collision_system="soft", on_target=ot, seed=11)
+    env = BatchedPogema(gc, num_envs=6, auto_reset="reseed")
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = [env.sample_actions(g) for _ in range(40)]
+    for t in range(15):                       # two reseeds happened: tasks differ from the initial ones
+        env.step(acts[t])
+    assert not np.array_equal(env.current_seeds(), env.seeds)
+    sd = env.state_dict()
+    seeds_at_save = env.current_seeds().copy()
+    obst_at_save = env.get_obstacles().copy()
+    want = [tuple(x.clone() for x in env.step(acts[t])) for t in range(15, 40)]
+    final = env.engine.checkpoint()
+    for target in (env, BatchedPogema(gc, num_envs=6, auto_reset="reseed")):
+        target.load_state_dict(sd)
+        assert np.array_equal(target.current_seeds(), seeds_at_save)
+        assert np.array_equal(target.get_obstacles(), obst_at_save)
+        for t in range(15, 40):
+            got = target.step(acts[t])
+            for x, y in zip(got, want[t - 15]):
+                assert torch.equal(x, y), (ot, t)
+        assert np.array_equal(target.engine.checkpoint(), final)
+
+
+def test_checkpoint_of_another_engine_is_rejected():
+    from pogema_b200 import BatchedPogema, GridConfig
+    from pogema_b200._native import PgmError
+    kw = dict(size=10, density=0.2, num_agents=6, obs_radius=2, max_episode_steps=8)
+    a = BatchedPogema(GridConfig(seed=1, **kw), num_envs=4)
+    blob = a.engine.checkpoint()
+    b = BatchedPogema(GridConfig(seed=1, collision_system="soft", **kw), num_envs=4)   # same byte size, other mode
+    with pytest.raises(PgmError, match="another engine"):
+        b.engine.restore(blob)
+    c = BatchedPogema(GridConfig(seed=2, **kw), num_envs=4)                           # same shape, other tasks
+    with pytest.raises(PgmError, match="different task seeds"):
+        c.engine.restore(blob)
+    with pytest.raises(PgmError, match="magic"):
+        a.engine.restore(np.zeros_like(blob))
+    a.engine.restore(blob)
+
+
+def test_action_dtypes_are_checked():
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    env = BatchedPogema(GridConfig(size=8, density=0.1, num_agents=3, obs_radius=2, seed=0), num_envs=2, auto_reset=False)
+    env.reset()
+    with pytest.raises(TypeError):
+        env.step_host(np.ones((2, 3), np.float64))
+    with pytest.raises(TypeError):
+        env.rollout(torch.ones((4, 2, 3), device="cuda"))
+    # wide integer actions are read in full: 256 / -256 do not alias to 'stay'
+    before = env.get_agents_xy().clone()
+    env.step(torch.full((2, 3), 256, dtype=torch.int32, device="cuda"))
+    with pytest.raises(IndexError):
+        env.check_errors()
+    env.step(torch.full((2, 3), -256, dtype=torch.int64, device="cuda"))
+    with pytest.raises(IndexError):
+        env.check_errors()
+    env.step(torch.full((2, 3), 0x0400, dtype=torch.int16, device="cuda"))
+    with pytest.raises(IndexError):
+        env.check_errors()
+    assert torch.equal(env.get_agents_xy(), before)        # invalid actions are treated as 'stay'
+
+
 def test_batched_metrics_match_oracle_wrappers():
     import torch
     from pogema_b200 import BatchedPogema, GridConfig

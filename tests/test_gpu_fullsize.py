@@ -90,13 +90,23 @@ def check_invariants(env, prev_xy=None, was_reset=None):
 
 
 def run_case(gc_kwargs, N, T, compare_oracle=True, team_threads=0, seed0=0):
+    """compare_oracle: True = C oracle on EVERY instance (lifelong configurations: built from the Python oracle's
+    own resets in a process pool - numpy generators, component tables; the others: from the engine's state after
+    reset, which tests/test_native_generator.py and test_gpu_devgen.py pin to the Python oracle)."""
     import torch
     from pogema_b200 import BatchedPogema, GridConfig
     env = BatchedPogema(GridConfig(**gc_kwargs), num_envs=N, seeds=np.arange(seed0, seed0 + N), auto_reset=True,
                         team_threads=team_threads)
     obs = env.reset()
     assert torch.equal(obs, torch_reference_obs(env))
-    co = c_oracle_from_engine(env) if compare_oracle else None
+    co = None
+    if compare_oracle and gc_kwargs.get("on_target") == "restart":
+        co = COracle.from_python_oracle_parallel(gc_kwargs, list(range(seed0, seed0 + N)))
+        r0 = gc_kwargs["obs_radius"]
+        assert np.array_equal(env.get_agents_xy().cpu().numpy() + r0, co.pos)   # same tasks to begin with
+        assert np.array_equal(env.get_targets_xy().cpu().numpy() + r0, co.tgt)
+    elif compare_oracle:
+        co = c_oracle_from_engine(env)
     g = torch.Generator(device="cuda").manual_seed(7)
     A = gc_kwargs["num_agents"]
     rsum = torch.zeros((N, A), dtype=torch.float64, device="cuda")
@@ -152,45 +162,34 @@ from pogema_b200.maps import maze_map, warehouse_map  # noqa: E402
 
 
 def test_config3_lifelong_maze_soft():
-    """configs[2]: 64x64 maze-like maps, 256 agents, soft collisions, on_target='restart'.
-    A subset of instances is checked against the Python-built C oracle (lifelong generators and
-    component tables come from numpy there); all 1024 are checked against the invariants and the
-    torch observation reference."""
-    import torch
-    from pogema_b200 import BatchedPogema, GridConfig
+    """configs[2]: 64x64 maze-like maps, 256 agents, soft collisions, on_target='restart': ALL 1024 instances
+    against the C oracle built from the Python oracle's resets (lifelong generators and component tables come
+    from numpy there), 72 steps = across the time-limit auto-reset at step 64; invariants and the torch
+    observation reference on the way."""
     m = maze_map(64, 3)
     gc = dict(map=m.tolist(), num_agents=256, obs_radius=5, max_episode_steps=64, collision_system="soft",
               on_target="restart")
-    N, T, K = 1024, 40, 6
-    env = BatchedPogema(GridConfig(**gc), num_envs=N, seeds=np.arange(N), auto_reset=True)
-    obs = env.reset()
-    assert torch.equal(obs, torch_reference_obs(env))
-    co = COracle.from_python_oracle(gc, list(range(K)))
-    g = torch.Generator(device="cuda").manual_seed(3)
-    prev = check_invariants(env)
-    acts = []
-    total_reward = 0.0
-    for t in range(T):
-        a = env.sample_actions(g)
-        acts.append(a[:K].cpu().numpy())
-        obs, rew, term, trunc = env.step(a)
-        total_reward += float(rew.sum())
-        assert not bool(term.any())
-        prev = check_invariants(env, prev, env.episode_done)
-    assert total_reward > 0                     # goals are reached and replaced
-    assert torch.equal(obs, torch_reference_obs(env))
-    out = co.run(np.stack(acts), auto_reset=True)
-    assert np.array_equal(env.get_agents_xy()[:K].cpu().numpy() + 5, co.pos)
-    assert np.array_equal(env.get_targets_xy()[:K].cpu().numpy() + 5, co.tgt)
-    assert np.array_equal(obs[:K].cpu().numpy(), out["obs"])
+    env, obs, rsum = run_case(gc, 1024, 72)
+    assert float(rsum.sum()) > 0                     # goals are reached and replaced
 
 
 def test_config4_warehouse_block_both():
-    """configs[3]: 256x256 warehouse-style maps, 1024 agents, block_both, r=5, 512 instances."""
+    """configs[3]: 256x256 warehouse-style maps, 1024 agents, block_both, r=5, 512 instances, 70 steps (across
+    the time-limit auto-reset), every instance against the C oracle."""
     m = warehouse_map(256)
     gc = dict(map=m.tolist(), num_agents=1024, obs_radius=5, max_episode_steps=64, collision_system="block_both",
               on_target="finish")
-    run_case(gc, 512, 12)
+    run_case(gc, 512, 70)
+
+
+@pytest.mark.parametrize("coll", ["priority", "block_both", "soft"])
+@pytest.mark.parametrize("ot", ["finish", "nothing", "restart"])
+def test_all_nine_modes_at_config2_full_size(coll, ot):
+    """All collision_system x on_target combinations at the configs[1] size (4096 x 64 agents, r=5), 70 steps,
+    every instance against the C oracle."""
+    gc = dict(size=32, density=0.3, num_agents=64, obs_radius=5, max_episode_steps=64,
+              collision_system=coll, on_target=ot)
+    run_case(gc, 4096, 70, seed0=7000)
 
 
 @pytest.mark.parametrize("r", [3, 5, 7])
