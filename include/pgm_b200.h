@@ -271,7 +271,9 @@ int64_t pgm_launch_count(const pgm_engine* e);
 
 /* Kernel plan actually chosen (for DESIGN.md / bench config): fills up to n ints:
  * [0] team_threads [1] teams_per_cta [2] cta_threads [3] smem_bytes_per_cta
- * [4] grid [5] agents_per_obs_batch [6] occupancy structure (0 dense cell grid, 1 tile buckets) */
+ * [4] grid [5] agents_per_obs_batch [6] occupancy structure (0 dense cell grid, 1 tile buckets)
+ * [7] 1 if step launches use the register-resident kernel for the common shapes (pgm_fast.cuh), then its
+ * [8] team_threads [9] agents per thread [10] teams_per_cta [11] smem_bytes_per_cta [12] grid */
 int pgm_plan(const pgm_engine* e, int32_t* out, int32_t n);
 
 #ifdef __cplusplus

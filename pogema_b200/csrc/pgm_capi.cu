@@ -70,6 +70,11 @@ struct pgm_engine {
   int team = 32, tpc = 1, cta_threads = 32, smem_cta = 0, grid = 0, batch_agents = 1, occ_mode = 0, obst_global = 0;
   int batch_single = 1;  // observation batch of single-step launches (pgm_step), <= batch_agents
   StepArgs layout{};  // offsets only
+  // fast path (pgm_fast.cuh): chosen by plan_fast() for the common shapes; step launches use it, reset / observe /
+  // odd caller pointers go through the generic kernel with the plan above
+  bool fast = false;
+  int f_team = 0, f_apt = 0, f_tpc = 1, f_cta_threads = 0, f_smem_cta = 0, f_grid = 0;
+  StepArgs f_layout{};
   // device state
   uint32_t* d_obst = nullptr;
   uint2 *d_state = nullptr, *d_state0 = nullptr;  // see pgm_kernels.cuh: x | active<<15 | y<<16 , target
@@ -87,7 +92,7 @@ struct pgm_engine {
   // d_obs_h / d_rew_h / d_term_h / d_trunc_h are parts of ONE device block (d_obs_h is its base); small results
   // (single instances behind the list API) come back with one copy into pinned staging and one synchronisation
   int64_t out_block_bytes = 0, off_rew = 0, off_term = 0, off_trunc = 0;
-  uint8_t* h_small = nullptr;  // pinned: [block | state NA*8 | was NA | actions NA*8], only if the block is <= kSmallBlock
+  uint8_t* h_small = nullptr;  // pinned: [block | state NA*8 | was NA | pad to 16 | actions NA*8], only if the block is <= kSmallBlock
   uint8_t* h_small_dev = nullptr;  // the same memory as the device sees it (zero-copy results of tiny engines)
   std::vector<uint2> h_state_tmp;
   // host mirrors
@@ -138,7 +143,8 @@ struct Layout {
   int occ_mode = 0, batch_agents = 0, team_smem = 0, obst_global = 0;
 };
 
-bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* out, bool obst_global = false) {
+bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* out, bool obst_global = false,
+                 int force_batch = 0) {
   const int A = e->cfg.num_agents;
   const int smem_max = 227 * 1024;
   int tiles = 0, tiles_w = 0, tshift = 0, occ_bytes;
@@ -175,6 +181,12 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   g = std::min<long long>(g, A);
   if (g < A && g > 32) g = g / 32 * 32;  // whole warps of agents per batch
   if (const char* v = getenv("PGM_OBS_BATCH")) g = std::max<long long>(1, std::min<long long>(g, atoi(v)));  // tuning knob
+  if (force_batch > 0) {
+    // the fast step kernel writes the packed stream in batches of its team size: the generic observe / reset
+    // launches of the same engine must use the same batch
+    g = std::min<long long>(A, force_batch);
+    if (fixed + std::max<long long>(occ_bytes, stage_bytes_for(g)) > smem_max) return false;
+  }
   const int stage_bytes = (int)stage_bytes_for(g);
   StepArgs& L = out->L;
   int off = 0;
@@ -209,6 +221,109 @@ bool make_layout(const pgm_engine* e, int occ_mode, int want_resident, Layout* o
   out->obst_global = obst_global ? 1 : 0;
   out->batch_agents = (int)g;
   out->team_smem = L.team_smem;
+  return true;
+}
+
+// teams per CTA: balance the busiest SM (CTAs are dealt round-robin, every SM should host the same
+// number of instances), prefer CTAs of 192..512 threads (measured: smaller CTAs cost ~15 %)
+int choose_tpc(const pgm_engine* e, int team, int team_smem) {
+  const int smem_max = 227 * 1024;
+  const pgm_config& c = e->cfg;
+  int max_tpc = std::min(1024 / team, std::max(1, smem_max / team_smem));
+  if (team > 32) max_tpc = std::min(max_tpc, 15);
+  int tpc = 1;
+  double best = -1.0;
+  const double ideal = (double)c.num_envs / e->sm_count;
+  for (int t = 1; t <= max_tpc; ++t) {
+    const int grid = (c.num_envs + t - 1) / t;
+    const int per_sm_ctas = (grid + e->sm_count - 1) / e->sm_count;
+    const double busiest = (double)per_sm_ctas * t;
+    double score = ideal / busiest;
+    const int threads = t * team;
+    if (threads < 192) score *= 0.85;
+    if (threads > 512) score *= 0.95;
+    score -= 1e-4 * std::abs(threads - 256) / 256.0;  // tie-break: closest to 256 threads
+    if (score > best) {
+      best = score;
+      tpc = t;
+    }
+  }
+  if (const char* v = getenv("PGM_TPC")) tpc = std::max(1, std::min(max_tpc, atoi(v)));  // tuning knob
+  return tpc;
+}
+
+// The fast step kernel (pgm_fast.cuh) for the common shapes: compile-time radius 2..7, uint8 / bits observations
+// whose per-instance block is a multiple of 16 bytes, at most 4 agents per thread, at most 8190 agents, both bitmaps
+// (and for priority / soft the uint16 cell grid) in shared memory at the residency the job wants.
+bool plan_fast(pgm_engine* e, int team, int want) {
+  const pgm_config& c = e->cfg;
+  const int A = c.num_agents;
+  if (const char* v = getenv("PGM_FAST")) {
+    if (v[0] == '0') return false;
+  }
+  if (c.obs_radius < 2 || c.obs_radius > 7) return false;
+  if (c.obs_format != PGM_OBS_U8 && c.obs_format != PGM_OBS_BITS) return false;
+  if (c.obs_format == PGM_OBS_U8 && ((int64_t)A * e->bits_per_agent) % 16 != 0) return false;
+  if (A > 8190 || e->obst_global) return false;
+  team = std::max(32, std::min(team, 256));
+  while ((A + team - 1) / team > 4 && team < 256) team *= 2;
+  int apt = (A + team - 1) / team;
+  if (apt > 4) return false;
+  if (apt == 3) apt = 4;
+  if (const char* v = getenv("PGM_FAST_TEAM")) {  // tuning knob
+    const int t = atoi(v);
+    if ((t == 32 || t == 64 || t == 128 || t == 256) && (A + t - 1) / t <= 4) {
+      team = t;
+      apt = (A + t - 1) / t;
+      if (apt == 3) apt = 4;
+    }
+  }
+  const int smem_max = 227 * 1024;
+  const int bitmap_bytes = round_up((e->PH * e->WPR + 1) * 4, 16);
+  const bool bb = c.collision_system == PGM_COLLISION_BLOCK_BOTH;
+  const int stage_one = round_up((team * e->stage_bpa + 31) / 32 * 4 + 16, 16);
+  auto build = [&](int bufs, StepArgs* L) {
+    int off = 0;
+    L->off_obst = off;
+    off += e->obst_stride * 4;
+    L->off_abits = off;
+    off += bitmap_bytes;
+    L->off_pbits = off;  // block_both: the second agent bitmap
+    if (bb) off += bitmap_bytes;
+    L->off_occ = off;
+    L->off_stage = off;  // block_both: the stream buffers lie over the claim planes (zeroed at the start of a step)
+    if (bb) {
+      off += std::max(2 * bitmap_bytes, bufs * stage_one);
+    } else {
+      off += round_up(e->PH * e->PW * 2, 16);
+      L->off_stage = off;
+      off += bufs * stage_one;
+    }
+    L->off_link = off;
+    if (!bb) off += round_up(apt * team * 4, 16);
+    L->off_npos = off;
+    if (!bb) off += round_up(apt * team * 4, 16);
+    L->off_misc = off;
+    off += 16;
+    L->team_smem = round_up(off, 16);
+    L->stage_bufs = bufs;
+    L->stage_words = stage_one / 4;
+    L->plane_words = bitmap_bytes / 4;
+    L->narrow = (e->WPR == 2 && c.width <= 32) ? 1 : 0;
+    return L->team_smem;
+  };
+  auto fit = [](int team_smem) { return (228 * 1024) / (team_smem + 1024); };
+  StepArgs L{};
+  int bufs = apt > 1 ? 2 : 1;
+  if (const char* v = getenv("PGM_FAST_BUFS")) bufs = atoi(v) > 1 ? 2 : 1;  // tuning knob
+  int sm = build(bufs, &L);
+  const int need = std::min(want, std::max(1, 1024 / team));
+  if (bufs == 2 && (sm > smem_max || fit(sm) < need)) sm = build(1, &L);
+  if (sm > smem_max) return false;
+  if (fit(sm) < std::min(need, 2) && want > 1) return false;  // the generic kernel's leaner layouts keep more instances resident
+  e->f_layout = L;
+  e->f_team = team;
+  e->f_apt = apt;
   return true;
 }
 
@@ -269,30 +384,23 @@ int compute_plan(pgm_engine* e) {
     e->batch_agents = std::max(team, A / 2);
   e->batch_single = e->batch_agents;
   if (!getenv("PGM_OBS_BATCH") && e->batch_agents == A && team <= 128 && A >= 2 * team) e->batch_single = std::max(team, A / 2);
-  // teams per CTA: balance the busiest SM (CTAs are dealt round-robin, every SM should host the same
-  // number of instances), prefer CTAs of 192..512 threads (measured: smaller CTAs cost ~15 %)
-  int max_tpc = std::min(1024 / team, std::max(1, smem_max / L.team_smem));
-  if (team > 32) max_tpc = std::min(max_tpc, 15);
-  int tpc = 1;
-  {
-    double best = -1.0;
-    const double ideal = (double)c.num_envs / e->sm_count;
-    for (int t = 1; t <= max_tpc; ++t) {
-      const int grid = (c.num_envs + t - 1) / t;
-      const int per_sm_ctas = (grid + e->sm_count - 1) / e->sm_count;
-      const double busiest = (double)per_sm_ctas * t;
-      double score = ideal / busiest;
-      const int threads = t * team;
-      if (threads < 192) score *= 0.85;
-      if (threads > 512) score *= 0.95;
-      score -= 1e-4 * std::abs(threads - 256) / 256.0;  // tie-break: closest to 256 threads
-      if (score > best) {
-        best = score;
-        tpc = t;
-      }
+  // the fast step kernel, if this shape has one; the generic launches of the engine then use its batch size
+  e->fast = false;
+  if (plan_fast(e, team, want)) {
+    Layout forced;
+    if (make_layout(e, use->occ_mode, want, &forced, use->obst_global != 0, e->f_team)) {
+      e->layout = forced.L;
+      e->batch_agents = forced.batch_agents;
+      e->batch_single = forced.batch_agents;
+      e->fast = true;
+      e->f_tpc = choose_tpc(e, e->f_team, e->f_layout.team_smem);
+      e->f_layout.teams_per_cta = e->f_tpc;
+      e->f_cta_threads = e->f_tpc * e->f_team;
+      e->f_smem_cta = e->f_tpc * e->f_layout.team_smem;
+      e->f_grid = (c.num_envs + e->f_tpc - 1) / e->f_tpc;
     }
   }
-  if (const char* v = getenv("PGM_TPC")) tpc = std::max(1, std::min(max_tpc, atoi(v)));  // tuning knob
+  const int tpc = choose_tpc(e, team, L.team_smem);
   e->tpc = tpc;
   L.teams_per_cta = tpc;
   e->cta_threads = tpc * team;
@@ -309,7 +417,40 @@ int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
   if (d.og && d.rt != 5) d.rt = 0;
   const int g = d.og ? (d.rt == 5 ? 1 : 0) : radius_group(d.rt);
   int err;
-  if (op == OP_OBSERVE) err = g ? launch_observe_g1(d, a, s) : launch_observe_g0(d, a, s);
+  // step launches of the common shapes: the register-resident kernel (uint8 observation blocks must be 16-byte aligned)
+  const bool fast = op == OP_STEP && e->fast &&
+                    (a.obs == nullptr || a.obs_format != 0 ||
+                     ((reinterpret_cast<uintptr_t>(a.obs) & 15u) == 0 && (a.obs_slot_stride & 15) == 0));
+  if (fast) {
+    StepArgs f = a;
+    const StepArgs& L = e->f_layout;
+    f.off_obst = L.off_obst;
+    f.off_abits = L.off_abits;
+    f.off_pbits = L.off_pbits;
+    f.off_occ = L.off_occ;
+    f.off_stage = L.off_stage;
+    f.off_link = L.off_link;
+    f.off_npos = L.off_npos;
+    f.off_misc = L.off_misc;
+    f.team_smem = L.team_smem;
+    f.teams_per_cta = L.teams_per_cta;
+    f.stage_bufs = L.stage_bufs;
+    f.stage_words = L.stage_words;
+    f.plane_words = L.plane_words;
+    f.narrow = L.narrow;
+    d.team = e->f_team;
+    d.apt = e->f_apt;
+    d.grid = e->f_grid;
+    d.block = e->f_cta_threads;
+    d.smem = e->f_smem_cta;
+    const int fg = d.rt >= 5 ? 1 : 0;
+    if (e->cfg.collision_system == PGM_COLLISION_PRIORITY)
+      err = fg ? launch_fast_priority_b(d, f, s) : launch_fast_priority_a(d, f, s);
+    else if (e->cfg.collision_system == PGM_COLLISION_BLOCK_BOTH)
+      err = fg ? launch_fast_block_both_b(d, f, s) : launch_fast_block_both_a(d, f, s);
+    else
+      err = fg ? launch_fast_soft_b(d, f, s) : launch_fast_soft_a(d, f, s);
+  } else if (op == OP_OBSERVE) err = g ? launch_observe_g1(d, a, s) : launch_observe_g0(d, a, s);
   else if (op == OP_RESET) err = g ? launch_reset_g1(d, a, s) : launch_reset_g0(d, a, s);
   else if (e->cfg.collision_system == PGM_COLLISION_PRIORITY)
     err = g ? launch_step_priority_g1(d, a, s) : launch_step_priority_g0(d, a, s);
@@ -479,7 +620,7 @@ int ensure_host_scratch(pgm_engine* e, int itemsize) {
     e->d_term_h = e->d_obs_h + e->off_term;
     e->d_trunc_h = e->d_obs_h + e->off_trunc;
     if (e->out_block_bytes <= kSmallBlock) {
-      CUDA_TRY(cudaHostAlloc((void**)&e->h_small, (size_t)e->out_block_bytes + NA * 17, cudaHostAllocMapped));
+      CUDA_TRY(cudaHostAlloc((void**)&e->h_small, (size_t)e->out_block_bytes + (NA * 9 + 15) / 16 * 16 + NA * 8, cudaHostAllocMapped));
       CUDA_TRY(cudaHostGetDevicePointer((void**)&e->h_small_dev, e->h_small, 0));
       if (e->out_block_bytes > 64 * 1024) e->h_small_dev = nullptr;  // beyond a few instances the copy engine is the better mover
       if (const char* v = getenv("PGM_ZERO_COPY")) {  // tuning knob: 0 = copy engine instead of direct stores
@@ -841,8 +982,11 @@ int64_t pgm_launch_count(const pgm_engine* e) { return e ? e->launches : 0; }
 
 int pgm_plan(const pgm_engine* e, int32_t* out, int32_t n) {
   if (!e || !out) return fail(PGM_ERR_INVALID, "null argument");
-  const int32_t v[7] = {e->team, e->tpc, e->cta_threads, e->smem_cta, e->grid, e->batch_agents, e->occ_mode};
-  for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
+  // [0..6] the generic kernel's plan; [7..12] the fast step kernel's (pgm_fast.cuh): 1 if step launches use it,
+  // team threads, agents per thread, teams per CTA, shared memory per CTA, grid
+  const int32_t v[13] = {e->team, e->tpc, e->cta_threads, e->smem_cta, e->grid, e->batch_agents, e->occ_mode,
+                         e->fast ? 1 : 0, e->f_team, e->f_apt, e->f_tpc, e->f_smem_cta, e->f_grid};
+  for (int i = 0; i < n && i < 13; ++i) out[i] = v[i];
   return PGM_OK;
 }
 
@@ -1139,11 +1283,12 @@ int pgm_step_host_ex(pgm_engine* e, const void* actions_host, int32_t action_ite
   if (zero_copy) {
     // a tiny engine (the list API's single instance): the kernel reads the actions from and writes its results to
     // pinned host memory itself - no copy engine round trips, only the launch and one wait
-    uint8_t* acts = e->h_small + e->out_block_bytes + NA * 9;
+    const size_t act_off = (size_t)e->out_block_bytes + (NA * 9 + 15) / 16 * 16;  // 16-byte aligned: wide actions are read in full
+    uint8_t* acts = e->h_small + act_off;
     memcpy(acts, actions_host, NA * action_itemsize);
     uint8_t* dv = e->h_small_dev;
     e->ovr_stream = false;
-    rc = pgm_step(e, dv + e->out_block_bytes + NA * 9, action_itemsize, obs_host ? dv : nullptr, (float*)(dv + e->off_rew),
+    rc = pgm_step(e, dv + act_off, action_itemsize, obs_host ? dv : nullptr, (float*)(dv + e->off_rew),
                   dv + e->off_term, dv + e->off_trunc, stream);
   } else {
     CUDA_TRY(cudaMemcpyAsync(e->d_act_h, actions_host, NA * action_itemsize, cudaMemcpyHostToDevice, s));

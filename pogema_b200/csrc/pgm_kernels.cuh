@@ -91,6 +91,11 @@ struct StepArgs {
   int team_smem;
   int teams_per_cta;
   int occ_tiles, occ_tiles_w, occ_tshift;  // OCC == 1: number of tiles (padded to 4), tiles per row, log2(tile side)
+  // pgm_fast_step_kernel (pgm_fast.cuh) only
+  int off_stage;    // observation stream buffers (stage_bufs of stage_words 32-bit words each)
+  int stage_bufs, stage_words;
+  int plane_words;  // block_both: words of one claim plane
+  int narrow;       // map at most 32 cells wide and two bitmap words per row: one 64-bit load per observation row
 };
 
 // ------------------------------------------------------------------------- //

@@ -10,17 +10,17 @@ namespace pgm {
 
 struct LaunchDims {
   int team, rt, grid, block, smem, device, pdl, occ, og;
+  int apt = 0;  // agents per thread of the fast kernel (pgm_fast.cuh)
 };
 
 // returns a cudaError_t as int
-template <int TEAM, int COLL, int OP, int RT, int OCC, int OG = 0>
-int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
-  auto kern = pgm_step_kernel<TEAM, COLL, OP, RT, OCC, OG>;
+template <typename Kern>
+int launch_kernel(Kern kern, std::atomic<unsigned long long>& configured, const LaunchDims& d, const StepArgs& a,
+                  cudaStream_t s) {
   // The attribute is per (function, device) and process-wide: set it once per device to the hardware maximum, so
   // engines of different shapes driven from different threads never lower each other's limit.
   constexpr int kMaxSmem = 227 * 1024;
-  static std::atomic<unsigned long long> configured{0ull};  // bit d = done for device d (devices >= 64: every launch)
-  const unsigned long long bit = d.device < 64 ? (1ull << d.device) : 0ull;
+  const unsigned long long bit = d.device < 64 ? (1ull << d.device) : 0ull;  // devices >= 64: every launch
   if (!(configured.load(std::memory_order_acquire) & bit) || bit == 0ull) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return (int)e;
@@ -39,6 +39,12 @@ int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return (int)cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+template <int TEAM, int COLL, int OP, int RT, int OCC, int OG = 0>
+int launch_exact(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
+  static std::atomic<unsigned long long> configured{0ull};
+  return launch_kernel(pgm_step_kernel<TEAM, COLL, OP, RT, OCC, OG>, configured, d, a, s);
 }
 
 // Radii with a compile-time specialisation are split in two groups (RTG) so that the variants of one
@@ -106,6 +112,14 @@ int launch_observe_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
 int launch_observe_g1(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
 int launch_reset_g0(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
 int launch_reset_g1(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+
+// pgm_fast_step_kernel variants, defined in pgm_inst_fast_*.cu (suffix = radius group: a = 2..4, b = 5..7)
+int launch_fast_priority_a(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_fast_priority_b(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_fast_block_both_a(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_fast_block_both_b(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_fast_soft_a(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
+int launch_fast_soft_b(const LaunchDims& d, const StepArgs& a, cudaStream_t s);
 
 // radii with a compile-time specialisation (1..7); every other radius runs the generic path
 inline int static_radius(int r) { return (r >= 1 && r <= 7) ? r : 0; }

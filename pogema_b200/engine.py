@@ -206,8 +206,14 @@ class Engine:
         return int(self.lib.pgm_launch_count(self.handle))
 
     def plan(self) -> dict:
-        out = (C.c_int32 * 7)()
-        nat.check(self.lib.pgm_plan(self.handle, out, 7))
+        out = (C.c_int32 * 13)()
+        nat.check(self.lib.pgm_plan(self.handle, out, 13))
         keys = ["team_threads", "teams_per_cta", "cta_threads", "smem_bytes_per_cta", "grid",
                 "agents_per_obs_batch", "occupancy_buckets"]
-        return dict(zip(keys, [int(v) for v in out]))
+        plan = dict(zip(keys, [int(v) for v in out[:7]]))
+        # step launches of the common shapes run the register-resident kernel (pgm_fast.cuh) with its own geometry
+        plan["fast_step_kernel"] = bool(out[7])
+        if out[7]:
+            plan["fast"] = dict(zip(["team_threads", "agents_per_thread", "teams_per_cta", "smem_bytes_per_cta", "grid"],
+                                    [int(v) for v in out[8:13]]))
+        return plan

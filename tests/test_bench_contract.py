@@ -35,6 +35,7 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_timed_steps_are_split_into_multi_step_launches_only():
+    # (the driver's --steps 20 goes out as one 20-step launch; longer runs are split by split_steps)
     sys.path.insert(0, ROOT)
     import bench
     assert bench.split_steps(20, 16) == [10, 10]           # the driver's --steps 20: no single-step remainder
