@@ -75,6 +75,9 @@ struct pgm_engine {
   bool fast = false;
   int f_team = 0, f_apt = 0, f_tpc = 1, f_cta_threads = 0, f_smem_cta = 0, f_grid = 0;
   StepArgs f_layout{};
+  uint8_t* d_fast_fill = nullptr;  // constant template the fast kernel's prologue copies into shared memory (TMA engine)
+  int fast_fill_bytes = 0;
+  int stagger_ns = 0;              // tuning knob PGM_STAGGER_NS (single-step launches of the fast kernel)
   // device state
   uint32_t* d_obst = nullptr;
   uint2 *d_state = nullptr, *d_state0 = nullptr;  // see pgm_kernels.cuh: x | active<<15 | y<<16 , target
@@ -438,6 +441,9 @@ int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
     f.stage_words = L.stage_words;
     f.plane_words = L.plane_words;
     f.narrow = L.narrow;
+    f.fill_src = e->d_fast_fill;
+    f.fill_bytes = e->fast_fill_bytes;
+    f.stagger_ns = a.num_steps == 1 ? e->stagger_ns : 0;
     d.team = e->f_team;
     d.apt = e->f_apt;
     d.grid = e->f_grid;
@@ -952,6 +958,20 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
     TRY_ALLOC(dev_alloc(&e->d_cells, (size_t)N * e->cells_stride));
   }
 #undef TRY_ALLOC
+  if (e->fast) {
+    // [zeros: one agent bitmap | 0xFF: the uint16 cell grid (priority / soft)], copied by cp.async.bulk
+    const int bitmap_bytes = round_up((e->PH * e->WPR + 1) * 4, 16);
+    const int grid_bytes = cfg->collision_system == PGM_COLLISION_BLOCK_BOTH ? 0 : round_up(e->PH * e->PW * 2, 16);
+    e->fast_fill_bytes = bitmap_bytes + grid_bytes;
+    std::vector<uint8_t> tmpl((size_t)e->fast_fill_bytes, 0xFF);
+    memset(tmpl.data(), 0, (size_t)bitmap_bytes);
+    if (cudaMalloc((void**)&e->d_fast_fill, tmpl.size()) != cudaSuccess ||
+        cudaMemcpy(e->d_fast_fill, tmpl.data(), tmpl.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      pgm_destroy(e);
+      return fail(PGM_ERR_CUDA, "allocating the fast kernel's fill template failed");
+    }
+    if (const char* v = getenv("PGM_STAGGER_NS")) e->stagger_ns = std::max(0, atoi(v));
+  }
   e->h_obst.assign((size_t)N * e->obst_stride, 0u);
   *out = e;
   return PGM_OK;
@@ -963,7 +983,8 @@ int pgm_destroy(pgm_engine* e) {
   void* ptrs[] = {e->d_obst,  e->d_state, e->d_state0, e->d_was,
                   e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
                   e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h /* base of the result block */,
-                  e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count};
+                  e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count,
+                  e->d_fast_fill};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete e->pool;

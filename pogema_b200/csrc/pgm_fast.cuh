@@ -169,31 +169,52 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
   pdl_trigger();
   PGM_STAMP(0);
   PGM_STAMP_NS(9);
-  // ---- prologue (independent of the previous launch): obstacle bitmap by bulk copy, shared-memory fills
+  // ---- prologue (independent of the previous launch): three bulk copies by the TMA engine fill the team's shared
+  // memory without an instruction of this warp - the instance's obstacle bitmap, and from a constant template
+  // (pgm_capi.cu :: fast_fill) the zeroed agent bitmap followed by the all-ones cell grid
   if (tid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
     const uint32_t bytes = (uint32_t)p.obst_stride * 4u;
-    mbar_expect_tx(s_bar, bytes);
+    mbar_expect_tx(s_bar, bytes + (uint32_t)p.fill_bytes);
     bulk_g2s(base + p.off_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
+    bulk_g2s(base + p.off_abits, p.fill_src, (uint32_t)p.fill_bytes, s_bar);
   }
   const int bm_vec = (p.PH * WPR + 1 + 3) >> 2;  // 16-byte vectors of one bitmap
   auto zero_bitmap = [&](uint32_t* bm) {
     uint4* b4 = reinterpret_cast<uint4*>(bm);
     for (int w = tid; w < bm_vec; w += TEAM) b4[w] = make_uint4(0u, 0u, 0u, 0u);
   };
-  if (COLL != 1) {
-    const int gvec = (p.PH * PW * 2 + 15) >> 4;
-    uint4* g4 = reinterpret_cast<uint4*>(s_grid);
-    for (int w = tid; w < gvec; w += TEAM) g4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
-  } else {
-    zero_bitmap(s_abits0);
-  }
   PGM_STAMP(1);
   pdl_wait();
   PGM_STAMP(2);
   PGM_STAMP_NS(10);
-  // ---- mutable state of this instance into registers
+  // single-step launches: teams of a CTA start a little apart, so that the first of them reach their store phase
+  // while the others still resolve moves (tuning knob)
+  if (p.stagger_ns > 0 && team > 0) __nanosleep((unsigned)(team * p.stagger_ns));
+  // ---- mutable state of this instance into registers; the first step's actions travel at the same time
+  const int isz = p.act_itemsize;
+  const uint8_t* act_ptr = p.actions + (ia + tid) * isz;  // this thread's first agent, step 0
+  auto issue_actions = [&](const uint8_t* ptr, uint32_t (&raw)[APT], const bool (&pres)[APT]) {
+    if (isz == 1) {
+#pragma unroll
+      for (int q = 0; q < APT; ++q) raw[q] = pres[q] ? (uint32_t)ptr[q * TEAM] : 0u;
+    } else {
+#pragma unroll
+      for (int q = 0; q < APT; ++q) raw[q] = pres[q] ? load_action(ptr, (long long)q * TEAM, isz) : 0u;
+    }
+  };
+  uint32_t pos[APT], tgt[APT], act[APT], raw_act[APT];
+  bool present[APT], active[APT];
+  uint2 w_in[APT];
+#pragma unroll
+  for (int q = 0; q < APT; ++q) {
+    const int a = q * TEAM + tid;
+    present[q] = a < A;
+    w_in[q] = make_uint2(0u, 0u);
+    if (present[q]) w_in[q] = p.state[ia + a];
+  }
+  issue_actions(act_ptr, raw_act, present);
   int step_idx = p.elapsed[n];
   int m_acc0, m_acc1, m_acc2;
   {
@@ -202,21 +223,16 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
     m_acc1 = m.y;
     m_acc2 = m.z;
   }
-  uint32_t pos[APT], tgt[APT], act[APT];
-  bool present[APT], active[APT];
 #pragma unroll
   for (int q = 0; q < APT; ++q) {
-    const int a = q * TEAM + tid;
-    present[q] = a < A;
-    uint2 w = make_uint2(0u, 0u);
-    if (present[q]) w = p.state[ia + a];
-    pos[q] = st_pos(w.x);
-    tgt[q] = w.y;
-    active[q] = present[q] && st_active(w.x) != 0u;
+    pos[q] = st_pos(w_in[q].x);
+    tgt[q] = w_in[q].y;
+    active[q] = present[q] && st_active(w_in[q].x) != 0u;
     act[q] = 0u;
   }
   int cur = 0;  // block_both: abits<cur> = occupancy before the move, abits<cur ^ 1> = after it
-  team_sync<TEAM>(bar_id);  // fills done; the mbarrier was initialised by thread 0 of the team
+  team_sync<TEAM>(bar_id);  // the mbarrier was initialised by thread 0 of the team
+  mbar_wait(s_bar, 0);
   if (COLL == 1) {
 #pragma unroll
     for (int q = 0; q < APT; ++q)
@@ -225,20 +241,21 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
         atomicOr(&s_abits0[x * WPR + (y >> 5)], 1u << (y & 31));
       }
   }
-  mbar_wait(s_bar, 0);
 
   const int num_steps = p.num_steps;
   int obs_slot = 0;
+  // per-thread output cursors: agent q of this thread sits q * TEAM elements further (a compile-time offset)
+  float* rew_ptr = p.rewards + (ia + tid);
+  uint8_t* term_ptr = p.terminated + (ia + tid);
+  uint8_t* trunc_ptr = p.truncated + (ia + tid);
 #pragma unroll 1
   for (int k = 0; k < num_steps; ++k) {
-    // ---- actions of step k
-    const uint8_t* act_k = p.actions + (long long)k * p.act_step_stride;
+    // ---- actions of step k (loaded one step ahead), then the loads of step k + 1 go out
     {
       bool bad = false;
 #pragma unroll
       for (int q = 0; q < APT; ++q) {
-        uint32_t v = 0u;
-        if (present[q]) v = load_action(act_k, ia + q * TEAM + tid, p.act_itemsize);
+        uint32_t v = raw_act[q];
         if (v > 4u) {
           bad = true;
           v = 0u;
@@ -246,6 +263,10 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
         act[q] = v;
       }
       if (bad) atomicOr(p.err_flag, 1);
+      if (k + 1 < num_steps) {
+        act_ptr += p.act_step_stride;
+        issue_actions(act_ptr, raw_act, present);
+      }
     }
     uint8_t* obs_k = p.obs;
     if (p.obs != nullptr) obs_k = p.obs + (long long)obs_slot * p.obs_slot_stride;
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
         cell[q] = (int)(pos[q] & 0xFFFF) * PW + (int)(pos[q] >> 16);
         if (active[q]) s_grid[cell[q]] = (uint16_t)((uint32_t)(q * TEAM + tid) | (act[q] << G_ACT));
       }
-      zero_bitmap(s_abits0);
+      if (k > 0) zero_bitmap(s_abits0);  // (first step: zeroed by the template copy)
       team_sync<TEAM>(bar_id);
       PGM_STAMP(3);
       if (COLL == 2) {
@@ -430,7 +451,6 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
     const bool done = trunc || all_term;
     const bool do_reset = done && p.auto_reset == 1;
     const bool reseed = done && p.auto_reset == 2;  // new task from a new seed: built after this launch
-    const long long oa = ia + (long long)k * p.out_step_stride;
     uint32_t* post = (COLL == 1 && cur) ? s_abits1 : s_abits0;
 #pragma unroll
     for (int q = 0; q < APT; ++q) {
@@ -457,9 +477,9 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
           p.rng[ia + a] = g;
         }
       }
-      p.rewards[oa + a] = rew;
-      p.terminated[oa + a] = term;
-      p.truncated[oa + a] = trunc ? 1 : 0;
+      rew_ptr[q * TEAM] = rew;
+      term_ptr[q * TEAM] = term;
+      trunc_ptr[q * TEAM] = trunc ? 1 : 0;
       p.was_on_goal[ia + a] = was[q] ? 1 : 0;
       uint32_t pp = npos[q];
       if (do_reset) {
@@ -508,6 +528,9 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
         *reinterpret_cast<int4*>(p.metric_acc + 4 * (long long)n) = make_int4(m_acc0, m_acc1, m_acc2, 0);
       }
     }
+    rew_ptr += p.out_step_stride;
+    term_ptr += p.out_step_stride;
+    trunc_ptr += p.out_step_stride;
     team_sync<TEAM>(bar_id);  // the agent bitmap is complete (and every thread is past the claim planes)
     PGM_STAMP(5);
 
@@ -533,7 +556,7 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
           fast_store_stream<NW>(stage, acc, (uint32_t)tid * sbpa, sbpa, present[q], g0 + tid + 1 < A && lane < 31, lane);
         }
         team_sync<TEAM>(bar_id);
-        if (q == 0) PGM_STAMP(7);
+        if (q == 0) PGM_STAMP(6);
         const int gcount = min(TEAM, A - g0);
         if (p.obs_format & 1) {
           // 1: bits, 32-bit words per agent;  3: the raw stream of the batch (packed host transport), batch q at
@@ -545,6 +568,7 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
         } else {
           fast_expand_u8<TEAM>(stage, obs_n + (long long)g0 * BPA, gcount * BPA, tid);
         }
+        if (q == 0) PGM_STAMP(7);
       }
     }
     PGM_STAMP(8);

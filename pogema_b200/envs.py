@@ -155,19 +155,24 @@ class GridView:
         return obstacles, agents_xy, targets_xy, active
 
 
-class Pogema(_Base):
-    """One POGEMA instance with the upstream list based API.  ``on_target``
-    selects the upstream class it stands for (finish -> Pogema, restart ->
-    PogemaLifeLong, nothing -> PogemaCoopFinish); the time limit
-    (MultiTimeLimit) and the metric wrappers are part of the same object."""
+class PogemaBase(_Base):
+    """One POGEMA instance with the upstream list based API (upstream envs.py :: PogemaBase + the step logic of
+    its three subclasses, which lives in the kernel: ``grid_config.on_target`` selects it).  The time limit
+    (MultiTimeLimit) and the metric wrappers are part of the same object.  Use the subclasses ``Pogema`` /
+    ``PogemaLifeLong`` / ``PogemaCoopFinish`` (or ``pogema_v0``) - like upstream's, each of them fixes its own
+    ``on_target`` semantics whatever the config says."""
 
     metadata = {"render_modes": ["ansi"]}
+    _ON_TARGET = None  # subclasses: the on_target mode the class stands for
 
     def __init__(self, grid_config: Optional[GridConfig] = None, device: int = 0, **kwargs):
         if grid_config is None:
             grid_config = GridConfig(**kwargs)
         elif isinstance(grid_config, dict):
             grid_config = GridConfig(**grid_config)
+        if self._ON_TARGET is not None and grid_config.on_target != self._ON_TARGET:
+            # upstream picks the semantics by CLASS: PogemaLifeLong(GridConfig(on_target='finish')) is lifelong
+            grid_config = grid_config.model_copy(update=dict(on_target=self._ON_TARGET))
         self.grid_config = grid_config
         self._device = int(device)
         self._engine = None
@@ -341,12 +346,26 @@ class Pogema(_Base):
             self._engine = None
 
 
-PogemaLifeLong = Pogema
-PogemaCoopFinish = Pogema
+class Pogema(PogemaBase):
+    """upstream envs.py :: Pogema - on_target='finish': an agent that reaches its goal is rewarded once and disappears."""
+    _ON_TARGET = 'finish'
+
+
+class PogemaLifeLong(PogemaBase):
+    """upstream envs.py :: PogemaLifeLong - on_target='restart': a reached goal is replaced by a new one."""
+    _ON_TARGET = 'restart'
+
+
+class PogemaCoopFinish(PogemaBase):
+    """upstream envs.py :: PogemaCoopFinish - on_target='nothing': reward when all agents stand on their goals."""
+    _ON_TARGET = 'nothing'
+
+
+_ENV_CLASSES = {'finish': Pogema, 'restart': PogemaLifeLong, 'nothing': PogemaCoopFinish}
 
 
 def _make_pogema(grid_config):
-    env = Pogema(grid_config)
+    env = _ENV_CLASSES[grid_config.on_target](grid_config)  # upstream integrations/make_pogema.py picks the class the same way
     if grid_config.persistent:  # upstream integrations/make_pogema.py :: _make_pogema
         from .wrappers import PersistentWrapper
         env = PersistentWrapper(env)

@@ -414,3 +414,26 @@ def test_c_abi_misuse_returns_status_codes():
     bad.abi_version = nat.PGM_ABI_VERSION
     bad.device, bad.num_envs, bad.num_agents, bad.height, bad.width, bad.obs_radius, bad.max_episode_steps = 99, 1, 1, 8, 8, 2, 8
     assert lib.pgm_create(C.byref(bad), C.byref(h)) == nat.PGM_ERR_INVALID                      # no such device
+
+
+def test_env_classes_fix_their_on_target_semantics():
+    """upstream: the CLASS decides the step semantics (PogemaLifeLong(GridConfig(on_target='finish')) is lifelong)."""
+    from pogema_b200 import GridConfig, Pogema, PogemaBase, PogemaCoopFinish, PogemaLifeLong, pogema_v0
+    gc = GridConfig(size=8, density=0.2, num_agents=3, obs_radius=2, seed=1, on_target="finish")
+    assert PogemaLifeLong(gc).grid_config.on_target == "restart"
+    assert PogemaCoopFinish(gc).grid_config.on_target == "nothing"
+    assert Pogema(gc.model_copy(update=dict(on_target="restart"))).grid_config.on_target == "finish"
+    for ot, cls in (("finish", Pogema), ("restart", PogemaLifeLong), ("nothing", PogemaCoopFinish)):
+        env = pogema_v0(gc.model_copy(update=dict(on_target=ot)))
+        assert type(env) is cls and isinstance(env, PogemaBase)
+    # lifelong semantics really run: nobody terminates, targets are replaced
+    env = PogemaLifeLong(gc)
+    ref = orc.pogema_v0(orc.GridConfig(size=8, density=0.2, num_agents=3, obs_radius=2, seed=1, on_target="restart"))
+    env.reset(), ref.reset()
+    rng = np.random.default_rng(0)
+    for t in range(40):
+        a = [int(x) for x in rng.integers(0, 5, size=3)]
+        o, r, te, tr, _ = env.step(a)
+        ro, rr, rte, rtr, _ = ref.step(a)
+        assert list(r) == list(rr) and list(te) == list(rte) and list(tr) == list(rtr)
+        assert all(np.array_equal(x, y) for x, y in zip(o, ro))

@@ -37,3 +37,28 @@ def test_seed_is_mutable():
     gc = GridConfig(seed=1)
     gc.seed = 7
     assert gc.seed == 7
+
+
+def test_gymnasium_registration_is_guarded():
+    """`Pogema-v0` is registered when gymnasium is importable and silently skipped when it is not."""
+    import importlib.util
+    import pogema_b200
+    have = importlib.util.find_spec("gymnasium") is not None
+    assert pogema_b200.GYMNASIUM_REGISTERED == have
+    if have:
+        import gymnasium
+        assert "Pogema-v0" in gymnasium.envs.registration.registry
+
+
+def test_pin_upstream_kit_runs():
+    """tools/pin_upstream.py: the probe reports, and the differential machinery agrees with itself."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "pin_upstream.py"), "--out", "/tmp/_pin_probe.txt"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "RESULT:" in out.stdout
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "pin_upstream.py"), "--self-test", "--seeds", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "episodes identical" in out.stdout, out.stdout + out.stderr

@@ -28,6 +28,8 @@ torch.cuda.synchronize()
 env.engine.lib.pgm_set_debug_buffer(env.engine.handle, None)
 d = dbg.cpu().numpy().astype(np.float64)
 names = ["start", "prologue", "pdl_wait", "load+occ+mbar", "resolve", "bookkeeping", "abits+zero", "gen", "expand+store"]
+if env.engine.plan().get("fast_step_kernel"):
+    names = ["start", "prologue fills", "pdl_wait", "state+actions+publish", "resolve", "bookkeeping+bitmap", "batch0 bits", "batch0 expand+store", "other batches"]
 # clock64 is per-SM: only differences within an instance are meaningful
 print("plan", env.engine.plan())
 prev = d[:, 0]
