@@ -9,9 +9,9 @@ BUILD := build
 LIB := pogema_b200/_lib/libpgm_b200.so
 INST := step_priority step_block_both step_soft observe reset
 FAST := priority block_both soft
-CU := pgm_capi pgm_devgen $(foreach i,$(INST),pgm_inst_$(i)_g0 pgm_inst_$(i)_g1) $(foreach i,$(FAST),pgm_inst_fast_$(i)_a pgm_inst_fast_$(i)_b)
+CU := pgm_capi pgm_plan pgm_transport pgm_devgen $(foreach i,$(INST),pgm_inst_$(i)_g0 pgm_inst_$(i)_g1) $(foreach i,$(FAST),pgm_inst_fast_$(i)_a pgm_inst_fast_$(i)_b)
 OBJS := $(addprefix $(BUILD)/,$(addsuffix .o,$(CU))) $(BUILD)/pgm_gen.o $(BUILD)/pgm_hostexpand.o
-HDRS := $(CSRC)/pgm_devgen.h $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_fast.cuh $(CSRC)/pgm_fast_launch.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h $(CSRC)/pgm_hostexpand.h include/pgm_b200.h
+HDRS := $(CSRC)/pgm_devgen.h $(CSRC)/pgm_kernels.cuh $(CSRC)/pgm_fast.cuh $(CSRC)/pgm_fast_launch.cuh $(CSRC)/pgm_launch.cuh $(CSRC)/pgm_engine.h $(CSRC)/pgm_rng.h $(CSRC)/pgm_gen.h $(CSRC)/pgm_hostexpand.h include/pgm_b200.h
 
 all: $(LIB) oracle
 

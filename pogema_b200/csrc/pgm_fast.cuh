@@ -1,7 +1,7 @@
 // pgm_fast.cuh - the register-resident step kernel for the common shapes (sm_100a).
 //
 // Same step semantics and the same outputs, bit for bit, as pgm_step_kernel (pgm_kernels.cuh), for the shapes
-// the planner marks `fast` (pgm_capi.cu :: plan_fast): compile-time radius 2..7, at most 4 agents per thread
+// the planner marks `fast` (pgm_plan.cu :: plan_fast): compile-time radius 2..7, at most 4 agents per thread
 // (APT), at most 8191 agents, uint8 / bit-packed observations, 16-byte aligned observation blocks.  What differs
 // is how the work is laid out - the generic kernel is bound by issue slots, not by HBM, on single-step launches
 // and on small radii (profiles/r01_single_step_instruction_mix.txt), so this one is written to issue less:
@@ -169,9 +169,15 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
   pdl_trigger();
   PGM_STAMP(0);
   PGM_STAMP_NS(9);
+  if (dbg != nullptr) {  // where this team runs: SM and hardware warp slot (tools/phase_timeline.py)
+    uint32_t smid, warpid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+    dbg[12] = (long long)((smid << 16) | warpid);
+  }
   // ---- prologue (independent of the previous launch): three bulk copies by the TMA engine fill the team's shared
   // memory without an instruction of this warp - the instance's obstacle bitmap, and from a constant template
-  // (pgm_capi.cu :: fast_fill) the zeroed agent bitmap followed by the all-ones cell grid
+  // (allocated by pgm_create, pgm_capi.cu) the zeroed agent bitmap followed by the all-ones cell grid
   if (tid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
@@ -556,7 +562,10 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
           fast_store_stream<NW>(stage, acc, (uint32_t)tid * sbpa, sbpa, present[q], g0 + tid + 1 < A && lane < 31, lane);
         }
         team_sync<TEAM>(bar_id);
-        if (q == 0) PGM_STAMP(6);
+        if (q == 0) {
+          PGM_STAMP(6);
+          PGM_STAMP_NS(13);
+        }
         const int gcount = min(TEAM, A - g0);
         if (p.obs_format & 1) {
           // 1: bits, 32-bit words per agent;  3: the raw stream of the batch (packed host transport), batch q at

@@ -38,7 +38,7 @@ int launch_fast_apt(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   }
 }
 
-// (team, agents per thread) pairs the planner may choose: see pgm_capi.cu :: plan_fast
+// (team, agents per thread) pairs the planner may choose: see pgm_plan.cu :: plan_fast
 template <int COLL, int RTG>
 int launch_fast_variant(const LaunchDims& d, const StepArgs& a, cudaStream_t s) {
   switch (d.team) {

@@ -48,3 +48,20 @@ print("launch wall clock (us): first CTA start 0.00 | last CTA start %.2f | depe
                                                          (np.percentile(t11, 95) - t0) / 1e3, (t11.max() - t0) / 1e3))
 work = (t11 - t10) / 1e3
 print("per-instance work after the wait (us): mean %.2f p50 %.2f p95 %.2f max %.2f" % (work.mean(), np.percentile(work, 50), np.percentile(work, 95), work.max()))
+
+if env.engine.plan().get("fast_step_kernel"):
+    first = (d[:, 13] - t10) / 1e3
+    print("first observation bytes ready, after the wait (us): p5 %.2f p50 %.2f p95 %.2f max %.2f" % tuple(np.percentile(first, [5, 50, 95, 100])))
+    fin = (t11 - t10.min()) / 1e3
+    hist, edges = np.histogram(fin, bins=10)
+    print("finish histogram (us after the wait):", " ".join("%.1f:%d" % (edges[i], hist[i]) for i in range(10)))
+    sm = (d[:, 12].astype(np.int64) >> 16); wid = d[:, 12].astype(np.int64) & 0xFFFF
+    per_sm = np.bincount(sm, minlength=148)
+    print("teams per SM: min %d max %d; SMs used %d" % (per_sm[per_sm > 0].min(), per_sm.max(), (per_sm > 0).sum()))
+    sub = np.zeros((int(sm.max()) + 1, 4), dtype=np.int64)
+    np.add.at(sub, (sm, wid & 3), 1)
+    print("warps per (SM, warp slot & 3): mean per slot-class", sub.mean(0).round(2), " worst SM", sub[sub.max(1).argmax()], " slot ids seen", np.unique(wid)[:40])
+    # finish time by SM: is the tail specific to some SMs?
+    fin_sm = np.array([fin[sm == k].max() if (sm == k).any() else 0 for k in range(int(sm.max()) + 1)])
+    order = np.argsort(fin_sm)
+    print("last finish per SM (us): min %.2f p50 %.2f max %.2f; slowest SMs %s" % (fin_sm[fin_sm > 0].min(), np.median(fin_sm[fin_sm > 0]), fin_sm.max(), order[-6:].tolist()))
