@@ -300,6 +300,11 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
       return fail(PGM_ERR_CUDA, "allocating the fast kernel's fill template failed");
     }
     if (const char* v = getenv("PGM_STAGGER_NS")) e->stagger_ns = std::max(0, atoi(v));
+    if (const char* v = getenv("PGM_FAST_TMAFILL")) e->fast_tma_fill = v[0] == '1';  // tuning knob
+    if (const char* v = getenv("PGM_FAST_MAXCTA")) {  // tuning knob: at most this many CTAs per SM in single-step launches
+      const int m = std::max(1, atoi(v));
+      e->f_single_pad = std::min(227 * 1024, (228 * 1024) / m - 1024) / 16 * 16;
+    }
   }
   e->h_obst.assign((size_t)N * e->obst_stride, 0u);
   *out = e;

@@ -184,13 +184,23 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
     const uint32_t bytes = (uint32_t)p.obst_stride * 4u;
     mbar_expect_tx(s_bar, bytes + (uint32_t)p.fill_bytes);
     bulk_g2s(base + p.off_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
-    bulk_g2s(base + p.off_abits, p.fill_src, (uint32_t)p.fill_bytes, s_bar);
+    if (p.fill_bytes > 0) bulk_g2s(base + p.off_abits, p.fill_src, (uint32_t)p.fill_bytes, s_bar);
   }
   const int bm_vec = (p.PH * WPR + 1 + 3) >> 2;  // 16-byte vectors of one bitmap
   auto zero_bitmap = [&](uint32_t* bm) {
     uint4* b4 = reinterpret_cast<uint4*>(bm);
     for (int w = tid; w < bm_vec; w += TEAM) b4[w] = make_uint4(0u, 0u, 0u, 0u);
   };
+  if (p.fill_bytes == 0) {
+    // the same fills by the team's own stores: shorter when the launch is not hidden under its predecessor (a
+    // bulk copy has ~1 us of latency, which small single-step launches see in full)
+    zero_bitmap(s_abits0);
+    if (COLL != 1) {
+      const int gvec = (p.PH * PW * 2 + 15) >> 4;
+      uint4* g4 = reinterpret_cast<uint4*>(s_grid);
+      for (int w = tid; w < gvec; w += TEAM) g4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+  }
   PGM_STAMP(1);
   pdl_wait();
   PGM_STAMP(2);

@@ -1,0 +1,29 @@
+#!/bin/bash
+# Round 2 evidence run (GPU box, under gpurun): bench lines in the driver's invocation and with defaults, the ncu
+# launch list of the same command, `ncu --set full` captures of the kernels behind every benchmarked configuration,
+# phase timelines, all configurations in both launch forms.  Raw outputs land in gpurun_out/r02_*; tools/
+# summarize_profiles_r02.py turns them into profiles/r02_*.
+set -x
+O=gpurun_out
+mkdir -p $O
+python bench.py --gpus 1 --steps 20 --warmup 5 > $O/r02_bench_driver.json 2> $O/r02_bench_driver.err
+python bench.py > $O/r02_bench.json 2> $O/r02_bench.err
+python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/r02_bench_reference.json 2>> $O/r02_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches.csv \
+    python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 3 > $O/r02_bench_under_ncu.log 2>&1
+NCU="ncu --set full --clock-control none --import-source on -k regex:pgm_fast"
+# configs[1]: the 3rd 16-step launch (after 20 single warm-up steps + 3 warm-up launches), and one single-step launch
+$NCU -s 24 -c 1 -o $O/r02_prof_c1_many python tools/quick_bench.py --steps 64 --many 16 > $O/r02_ncu_c1_many.log 2>&1
+$NCU -s 30 -c 1 -o $O/r02_prof_c1_single python tools/quick_bench.py --steps 32 > $O/r02_ncu_c1_single.log 2>&1
+# configs[2] maze soft/restart, configs[3] warehouse block_both, configs[4] r=3 share: one 16-step launch each
+$NCU -s 24 -c 1 -o $O/r02_prof_c2_many python tools/quick_bench.py --n 1024 --size 64 --agents 256 --coll soft --ot restart --map maze --steps 64 --many 16 > $O/r02_ncu_c2_many.log 2>&1
+$NCU -s 24 -c 1 -o $O/r02_prof_c3_many python tools/quick_bench.py --n 512 --size 256 --agents 1024 --coll block_both --map warehouse --steps 64 --many 16 > $O/r02_ncu_c3_many.log 2>&1
+$NCU -s 24 -c 1 -o $O/r02_prof_r3_many python tools/quick_bench.py --n 2048 --r 3 --steps 64 --many 16 > $O/r02_ncu_r3_many.log 2>&1
+$NCU -s 30 -c 1 -o $O/r02_prof_r3_single python tools/quick_bench.py --n 2048 --r 3 --steps 32 > $O/r02_ncu_r3_single.log 2>&1
+python tools/phase_timeline.py > $O/r02_timeline_c1.txt 2>&1
+python tools/phase_timeline.py --n 2048 --r 3 > $O/r02_timeline_r3.txt 2>&1
+python tools/phase_timeline.py --n 512 --size 256 --agents 1024 --coll block_both --map warehouse > $O/r02_timeline_c3.txt 2>&1
+python tools/bench_configs.py > $O/r02_configs.json 2> $O/r02_configs.err
+bash tools/gpu/r02_b_san.sh > $O/r02_sanitizer_fast.log 2>&1
+bash tools/sanitize.sh > $O/r02_sanitizer_generic.log 2>&1
+ls -la $O | grep r02_
