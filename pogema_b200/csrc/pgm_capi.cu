@@ -287,25 +287,6 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
     TRY_ALLOC(dev_alloc(&e->d_cells, (size_t)N * e->cells_stride));
   }
 #undef TRY_ALLOC
-  if (e->fast) {
-    // [zeros: one agent bitmap | 0xFF: the uint16 cell grid (priority / soft)], copied by cp.async.bulk
-    const int bitmap_bytes = round_up((e->PH * e->WPR + 1) * 4, 16);
-    const int grid_bytes = cfg->collision_system == PGM_COLLISION_BLOCK_BOTH ? 0 : round_up(e->PH * e->PW * 2, 16);
-    e->fast_fill_bytes = bitmap_bytes + grid_bytes;
-    std::vector<uint8_t> tmpl((size_t)e->fast_fill_bytes, 0xFF);
-    memset(tmpl.data(), 0, (size_t)bitmap_bytes);
-    if (cudaMalloc((void**)&e->d_fast_fill, tmpl.size()) != cudaSuccess ||
-        cudaMemcpy(e->d_fast_fill, tmpl.data(), tmpl.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-      pgm_destroy(e);
-      return fail(PGM_ERR_CUDA, "allocating the fast kernel's fill template failed");
-    }
-    if (const char* v = getenv("PGM_STAGGER_NS")) e->stagger_ns = std::max(0, atoi(v));
-    if (const char* v = getenv("PGM_FAST_TMAFILL")) e->fast_tma_fill = v[0] == '1';  // tuning knob
-    if (const char* v = getenv("PGM_FAST_MAXCTA")) {  // tuning knob: at most this many CTAs per SM in single-step launches
-      const int m = std::max(1, atoi(v));
-      e->f_single_pad = std::min(227 * 1024, (228 * 1024) / m - 1024) / 16 * 16;
-    }
-  }
   e->h_obst.assign((size_t)N * e->obst_stride, 0u);
   *out = e;
   return PGM_OK;
@@ -317,8 +298,7 @@ int pgm_destroy(pgm_engine* e) {
   void* ptrs[] = {e->d_obst,  e->d_state, e->d_state0, e->d_was,
                   e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
                   e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h /* base of the result block */,
-                  e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count,
-                  e->d_fast_fill};
+                  e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   free_transport(e);

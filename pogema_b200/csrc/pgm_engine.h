@@ -70,11 +70,6 @@ struct pgm_engine {
   bool fast = false;
   int f_team = 0, f_apt = 0, f_tpc = 1, f_cta_threads = 0, f_smem_cta = 0, f_grid = 0;
   pgm::StepArgs f_layout{};
-  int f_single_pad = 0;  // single-step launches: dynamic shared memory is padded to this, which caps the CTAs per SM
-  uint8_t* d_fast_fill = nullptr;  // constant template the fast kernel's prologue copies into shared memory (TMA engine)
-  int fast_fill_bytes = 0;
-  bool fast_tma_fill = false;  // prologue fills by bulk copy from the template instead of the team's own stores
-  int stagger_ns = 0;              // tuning knob PGM_STAGGER_NS (single-step launches of the fast kernel)
   // device state
   uint32_t* d_obst = nullptr;
   uint2 *d_state = nullptr, *d_state0 = nullptr;  // see pgm_kernels.cuh: x | active<<15 | y<<16 , target

@@ -16,8 +16,9 @@
 //   * observations: a thread assembles its agent's 3*D*D bits in registers, shifts them to the agent's offset in
 //     the batch bit stream and stores whole words; the word two neighbouring agents share travels by warp shuffle.
 //     No zero fill and no atomics on the stream (the generic kernel spends 10 ATOMS per warp and step there);
-//   * an observation batch is one agent per thread (TEAM agents), double buffered: the byte expansion + 16-byte
-//     streaming stores of batch q overlap the bit assembly of batch q + 1 of other warps.
+//   * an observation batch is one agent per thread; a warp's 32 agents are a word-aligned piece of the batch stream,
+//     so each warp assembles, expands and stores its own piece (16-byte streaming stores, 512 contiguous bytes per
+//     instruction) without a team barrier: the stores of one warp overlap the bit assembly of the others.
 //
 // Upstream symbols restated: see pgm_kernels.cuh (same list; /root/reference holds only README.md:1-5).
 #pragma once
@@ -116,7 +117,10 @@ __device__ __forceinline__ void fast_store_stream(uint32_t* stage, const uint32_
   }
 }
 
-// Expansion of `nbytes` stream bits (a multiple of 16, 16-byte aligned destination) into uint8 0/1.
+// Expansion of `nbytes` stream bits (a multiple of 16, 16-byte aligned destination) into uint8 0/1: a lane turns
+// 16 stream bits into 16 bytes ((nibble * 0x00204081) & 0x01010101 per word) and issues one 16-byte streaming store;
+// a warp writes 512 contiguous bytes per instruction.  (A 256-entry shared-memory table byte -> 8 bytes halves the
+// instructions of this loop and was measured 10-30 % SLOWER: the two extra 64-bit loads per store bank-conflict.)
 template <int TEAM>
 __device__ __forceinline__ void fast_expand_u8(const uint32_t* stage, uint8_t* out, int nbytes, int tid) {
   const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
@@ -175,39 +179,33 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
     asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
     dbg[12] = (long long)((smid << 16) | warpid);
   }
-  // ---- prologue (independent of the previous launch): three bulk copies by the TMA engine fill the team's shared
-  // memory without an instruction of this warp - the instance's obstacle bitmap, and from a constant template
-  // (allocated by pgm_create, pgm_capi.cu) the zeroed agent bitmap followed by the all-ones cell grid
+  // ---- prologue (independent of the previous launch): the obstacle bitmap comes by bulk copy (TMA engine), the
+  // team zeroes its agent bitmap and sets every cell of the grid to "nobody" with its own 16-byte stores.  (Filling
+  // them by a second bulk copy from a constant template saves ~70 instructions per warp and was measured SLOWER on
+  // small single-step launches, 6.4 -> 7.0 us for 2048 instances at r=3: a bulk copy has ~1 us of latency, and a
+  // launch that cannot become resident under its predecessor sees all of it.)
   if (tid == 0) {
     mbar_init(s_bar, 1);
     fence_mbar_init();
     const uint32_t bytes = (uint32_t)p.obst_stride * 4u;
-    mbar_expect_tx(s_bar, bytes + (uint32_t)p.fill_bytes);
+    mbar_expect_tx(s_bar, bytes);
     bulk_g2s(base + p.off_obst, p.obst + (long long)n * p.obst_stride, bytes, s_bar);
-    if (p.fill_bytes > 0) bulk_g2s(base + p.off_abits, p.fill_src, (uint32_t)p.fill_bytes, s_bar);
   }
   const int bm_vec = (p.PH * WPR + 1 + 3) >> 2;  // 16-byte vectors of one bitmap
   auto zero_bitmap = [&](uint32_t* bm) {
     uint4* b4 = reinterpret_cast<uint4*>(bm);
     for (int w = tid; w < bm_vec; w += TEAM) b4[w] = make_uint4(0u, 0u, 0u, 0u);
   };
-  if (p.fill_bytes == 0) {
-    // the same fills by the team's own stores: shorter when the launch is not hidden under its predecessor (a
-    // bulk copy has ~1 us of latency, which small single-step launches see in full)
-    zero_bitmap(s_abits0);
-    if (COLL != 1) {
-      const int gvec = (p.PH * PW * 2 + 15) >> 4;
-      uint4* g4 = reinterpret_cast<uint4*>(s_grid);
-      for (int w = tid; w < gvec; w += TEAM) g4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
+  zero_bitmap(s_abits0);
+  if (COLL != 1) {
+    const int gvec = (p.PH * PW * 2 + 15) >> 4;
+    uint4* g4 = reinterpret_cast<uint4*>(s_grid);
+    for (int w = tid; w < gvec; w += TEAM) g4[w] = make_uint4(~0u, ~0u, ~0u, ~0u);
   }
   PGM_STAMP(1);
   pdl_wait();
   PGM_STAMP(2);
   PGM_STAMP_NS(10);
-  // single-step launches: teams of a CTA start a little apart, so that the first of them reach their store phase
-  // while the others still resolve moves (tuning knob)
-  if (p.stagger_ns > 0 && team > 0) __nanosleep((unsigned)(team * p.stagger_ns));
   // ---- mutable state of this instance into registers; the first step's actions travel at the same time
   const int isz = p.act_itemsize;
   const uint8_t* act_ptr = p.actions + (ia + tid) * isz;  // this thread's first agent, step 0
@@ -301,8 +299,10 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
         cell[q] = (int)(pos[q] & 0xFFFF) * PW + (int)(pos[q] >> 16);
         if (active[q]) s_grid[cell[q]] = (uint16_t)((uint32_t)(q * TEAM + tid) | (act[q] << G_ACT));
       }
-      if (k > 0) zero_bitmap(s_abits0);  // (first step: zeroed by the template copy)
       team_sync<TEAM>(bar_id);
+      // (every warp of the team is past its previous observation phase now: the agent bitmap may be cleared; the
+      // barriers of the resolution phase order this before the atomicOr's of phase 3)
+      if (k > 0) zero_bitmap(s_abits0);  // (first step: zeroed in the prologue)
       PGM_STAMP(3);
       if (COLL == 2) {
         // soft, pass A: moves into obstacles and edge swaps become 'stay' (judged on the raw actions)
@@ -550,16 +550,20 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
     team_sync<TEAM>(bar_id);  // the agent bitmap is complete (and every thread is past the claim planes)
     PGM_STAMP(5);
 
-    // ---- phase 4: observations, one batch = one agent per thread
+    // ---- phase 4: observations.  A batch is one agent per thread; a WARP's 32 agents are a word-aligned piece of the
+    // batch stream (32 * bits_per_agent bits = bits_per_agent words), so every warp assembles, expands and stores its
+    // own piece without waiting for the other warps of the team: no team barrier in this phase
     if (obs_k != nullptr) {
       const uint32_t sbpa = (uint32_t)p.stage_bpa;
       uint8_t* obs_n = obs_k + (long long)n * p.obs_inst_stride;
+      const int warp = tid >> 5;
+      uint32_t* wstage = s_stage + (uint32_t)warp * sbpa;  // this warp's sbpa words
 #pragma unroll
       for (int q = 0; q < APT; ++q) {
-        const int g0 = q * TEAM;
-        if (g0 >= A) break;  // team-uniform
-        uint32_t* stage = s_stage + ((p.stage_bufs > 1 && (q & 1)) ? p.stage_words : 0);
-        if (q > 0 && p.stage_bufs == 1) team_sync<TEAM>(bar_id);
+        const int wfirst = q * TEAM + (warp << 5);          // first agent of this warp's piece
+        if (wfirst >= A) break;                             // warp-uniform
+        const int cnt = min(32, A - wfirst);
+        if (q > 0) __syncwarp();                            // the piece of the previous batch has been read
         {
           uint32_t acc[NW];
           if (present[q]) {
@@ -569,30 +573,30 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
 #pragma unroll
             for (int i = 0; i < NW; ++i) acc[i] = 0u;
           }
-          fast_store_stream<NW>(stage, acc, (uint32_t)tid * sbpa, sbpa, present[q], g0 + tid + 1 < A && lane < 31, lane);
+          fast_store_stream<NW>(wstage, acc, (uint32_t)lane * sbpa, sbpa, present[q], lane + 1 < cnt, lane);
         }
-        team_sync<TEAM>(bar_id);
+        __syncwarp();
         if (q == 0) {
           PGM_STAMP(6);
           PGM_STAMP_NS(13);
         }
-        const int gcount = min(TEAM, A - g0);
         if (p.obs_format & 1) {
-          // 1: bits, 32-bit words per agent;  3: the raw stream of the batch (packed host transport), batch q at
-          // the word offset its first agent has in format 1
+          // 1: bits, 32-bit words per agent;  3: the raw stream of the batch (packed host transport): batch q starts at
+          // the word its first agent has in format 1, this warp's piece `warp * bits_per_agent` words further
           constexpr int WPA = (BPA + 31) >> 5;
-          uint32_t* out = reinterpret_cast<uint32_t*>(obs_n) + (long long)g0 * WPA;
-          const int nw = (gcount * (int)sbpa + 31) >> 5;
-          for (int w = tid; w < nw; w += TEAM) __stcs(out + w, stage[w]);
+          uint32_t* out = reinterpret_cast<uint32_t*>(obs_n) + (long long)(q * TEAM) * WPA + (uint32_t)warp * sbpa;
+          const int nw = (cnt * (int)sbpa + 31) >> 5;
+          for (int w = lane; w < nw; w += 32) __stcs(out + w, wstage[w]);
         } else {
-          fast_expand_u8<TEAM>(stage, obs_n + (long long)g0 * BPA, gcount * BPA, tid);
+          fast_expand_u8<32>(wstage, obs_n + (long long)wfirst * BPA, cnt * BPA, lane);
         }
         if (q == 0) PGM_STAMP(7);
       }
     }
     PGM_STAMP(8);
     PGM_STAMP_NS(11);
-    if (k + 1 < num_steps) team_sync<TEAM>(bar_id);  // the stage buffers (and, for block_both, the planes under them) are reused
+    // block_both: the next step zeroes the claim planes, which lie under the stream pieces
+    if (COLL == 1 && k + 1 < num_steps) team_sync<TEAM>(bar_id);
   }
 }
 

@@ -96,9 +96,6 @@ struct StepArgs {
   int stage_bufs, stage_words;
   int plane_words;  // block_both: words of one claim plane
   int narrow;       // map at most 32 cells wide and two bitmap words per row: one 64-bit load per observation row
-  const uint8_t* fill_src;  // constant template: zeros (one agent bitmap) followed by 0xFF (the cell grid)
-  int fill_bytes;           // bytes of it copied to off_abits by the TMA engine in the prologue
-  int stagger_ns;           // single-step launches: team t of a CTA starts t * stagger_ns late (0 = off)
 };
 
 // ------------------------------------------------------------------------- //

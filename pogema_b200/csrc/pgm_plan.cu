@@ -192,11 +192,8 @@ bool plan_fast(pgm_engine* e, int team, int want) {
   };
   auto fit = [](int team_smem) { return (228 * 1024) / (team_smem + 1024); };
   StepArgs L{};
-  int bufs = apt > 1 ? 2 : 1;
-  if (const char* v = getenv("PGM_FAST_BUFS")) bufs = atoi(v) > 1 ? 2 : 1;  // tuning knob
-  int sm = build(bufs, &L);
   const int need = std::min(want, std::max(1, 1024 / team));
-  if (bufs == 2 && (sm > smem_max || fit(sm) < need)) sm = build(1, &L);
+  const int sm = build(1, &L);  // one stream buffer: every warp owns its piece of it (no double buffering needed)
   if (sm > smem_max) return false;
   if (fit(sm) < std::min(need, 2) && want > 1) return false;  // the generic kernel's leaner layouts keep more instances resident
   e->f_layout = L;
@@ -317,15 +314,11 @@ int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
     f.stage_words = L.stage_words;
     f.plane_words = L.plane_words;
     f.narrow = L.narrow;
-    f.fill_src = e->d_fast_fill;
-    f.fill_bytes = e->fast_tma_fill ? e->fast_fill_bytes : 0;
-    f.stagger_ns = a.num_steps == 1 ? e->stagger_ns : 0;
     d.team = e->f_team;
     d.apt = e->f_apt;
     d.grid = e->f_grid;
     d.block = e->f_cta_threads;
     d.smem = e->f_smem_cta;
-    if (a.num_steps == 1 && e->f_single_pad > d.smem) d.smem = e->f_single_pad;  // residency cap of single-step launches
     const int fg = d.rt >= 5 ? 1 : 0;
     if (e->cfg.collision_system == PGM_COLLISION_PRIORITY)
       err = fg ? launch_fast_priority_b(d, f, s) : launch_fast_priority_a(d, f, s);
