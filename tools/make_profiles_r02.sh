@@ -26,4 +26,20 @@ python tools/phase_timeline.py --n 512 --size 256 --agents 1024 --coll block_bot
 python tools/bench_configs.py > $O/r02_configs.json 2> $O/r02_configs.err
 bash tools/gpu/r02_b_san.sh > $O/r02_sanitizer_fast.log 2>&1
 bash tools/sanitize.sh > $O/r02_sanitizer_generic.log 2>&1
-ls -la $O | grep r02_
+# summarise the captures HERE (gpurun brings back at most 64 MiB): text summaries stay, of the reports only configs[1]'s
+python - <<'PY'
+import subprocess, sys
+D = lambda r: 2 * r + 1
+bpa = lambda r, A, ph, pw: 3 * D(r) ** 2 + 21 + ((ph * pw + 7) // 8) / A
+caps = [("c1_many", "configs[1] (4096 x 64 agents, r=5, priority/finish): ONE 16-step launch (pgm_step_many)", 16 * 4096 * 64, bpa(5, 64, 42, 42)),
+        ("c1_single", "configs[1]: ONE single-step launch (pgm_step, the closed-loop form)", 4096 * 64, bpa(5, 64, 42, 42)),
+        ("c2_many", "configs[2] (1024 x 256 agents, 64x64 maze, soft/restart): ONE 16-step launch", 16 * 1024 * 256, bpa(5, 256, 74, 74)),
+        ("c3_many", "configs[3] (512 x 1024 agents, 256x256 warehouse, block_both): ONE 16-step launch", 16 * 512 * 1024, bpa(5, 1024, 266, 266)),
+        ("r3_many", "configs[4] r=3 share (2048 x 64 agents): ONE 16-step launch", 16 * 2048 * 64, bpa(3, 64, 38, 38)),
+        ("r3_single", "configs[4] r=3 share: ONE single-step launch", 2048 * 64, bpa(3, 64, 38, 38))]
+for tag, title, units, b in caps:
+    out = subprocess.run([sys.executable, "tools/ncu_summary.py", f"gpurun_out/r02_prof_{tag}.ncu-rep", title, str(units), str(b)], capture_output=True, text=True)
+    open(f"gpurun_out/r02_ncu_{tag}.txt", "w").write(out.stdout + (("\nSTDERR\n" + out.stderr[-2000:]) if out.returncode else ""))
+PY
+rm -f $O/r02_prof_c2_many.ncu-rep $O/r02_prof_c3_many.ncu-rep $O/r02_prof_r3_many.ncu-rep $O/r02_prof_r3_single.ncu-rep $O/r02_prof_c1_single.ncu-rep
+ls -la $O | grep r02_; du -sh $O

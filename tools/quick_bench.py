@@ -19,6 +19,7 @@ ap.add_argument("--map", default="random", choices=["random", "maze", "warehouse
 ap.add_argument("--max-steps", type=int, default=64)
 ap.add_argument("--graph", type=int, default=0)
 ap.add_argument("--many", type=int, default=0, help="steps per launch (pgm_step_many)")
+ap.add_argument("--ring", type=int, default=4, help="observation buffers written in turn (1: the same buffer every step - it may stay in L2)")
 a = ap.parse_args()
 from pogema_b200.maps import maze_map, warehouse_map
 mp = None if a.map == "random" else (maze_map(a.size, 3) if a.map == "maze" else warehouse_map(a.size)).tolist()
@@ -29,9 +30,9 @@ env = BatchedPogema(gc, num_envs=a.n, auto_reset=True, team_threads=a.team, obs_
 t_gen = time.time() - t0
 env.reset()
 acts = [env.sample_actions() for _ in range(16)]
-bufs = [env.new_obs_buffer() for _ in range(4)]
+bufs = [env.new_obs_buffer() for _ in range(a.ring)]
 for i in range(20):
-    env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
+    env.step(acts[i % 16], out=bufs[i % a.ring], compute_obs=not a.noobs)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 if a.many:
@@ -53,7 +54,7 @@ elif a.graph:
     with torch.cuda.stream(side):
         with torch.cuda.graph(g, stream=side):
             for i in range(a.graph):
-                env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
+                env.step(acts[i % 16], out=bufs[i % a.ring], compute_obs=not a.noobs)
     torch.cuda.synchronize()
     g.replay(); torch.cuda.synchronize()
     reps = max(1, a.steps // a.graph)
@@ -65,7 +66,7 @@ elif a.graph:
 else:
     e0.record()
     for i in range(a.steps):
-        env.step(acts[i % 16], out=bufs[i % 4], compute_obs=not a.noobs)
+        env.step(acts[i % 16], out=bufs[i % a.ring], compute_obs=not a.noobs)
     e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps

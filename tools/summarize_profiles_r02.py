@@ -22,21 +22,12 @@ for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
 open(f"{P}/r02_launch_summary.csv", "w").write("\n".join(lines) + "\n")
 shutil.copy(f"{G}/r02_launches.csv", f"{P}/r02_launches.csv")
 
-caps = [("c1_many", "configs[1] (4096 x 64 agents, r=5, priority/finish): ONE 16-step launch (pgm_step_many)", 16 * 4096 * 64, bpa(5, 64, 42, 42)),
-        ("c1_single", "configs[1]: ONE single-step launch (pgm_step, the closed-loop form)", 4096 * 64, bpa(5, 64, 42, 42)),
-        ("c2_many", "configs[2] (1024 x 256 agents, 64x64 maze, soft/restart): ONE 16-step launch", 16 * 1024 * 256, bpa(5, 256, 74, 74)),
-        ("c3_many", "configs[3] (512 x 1024 agents, 256x256 warehouse, block_both): ONE 16-step launch", 16 * 512 * 1024, bpa(5, 1024, 266, 266)),
-        ("r3_many", "configs[4] r=3 share (2048 x 64 agents): ONE 16-step launch", 16 * 2048 * 64, bpa(3, 64, 38, 38)),
-        ("r3_single", "configs[4] r=3 share: ONE single-step launch", 2048 * 64, bpa(3, 64, 38, 38))]
-for tag, title, units, b in caps:
-    rep = f"{G}/r02_prof_{tag}.ncu-rep"
-    if not os.path.exists(rep):
-        print("missing", rep); continue
-    out = subprocess.run([sys.executable, "tools/ncu_summary.py", rep, title, str(units), str(b)], capture_output=True, text=True).stdout
-    open(f"{P}/r02_ncu_{tag}.txt", "w").write(out)
-    if tag == "c1_many":
+import glob
+for f in sorted(glob.glob(f"{G}/r02_ncu_*.txt")):
+    out = open(f).read()
+    shutil.copy(f, f"{P}/" + os.path.basename(f))
+    if f.endswith("r02_ncu_c1_many.txt"):
         m = re.search(r"dram traffic \(read\+write\): ([0-9.]+) MB", out)
-        rd = re.search(r"dram__bytes_read.sum\s+(\S+)\s+(\S+)", out); wr = re.search(r"dram__bytes_write.sum\s+(\S+)\s+(\S+)", out)
         if m:
             json.dump({"dram_bytes_per_launch": float(m.group(1)) * 1e6, "steps_per_launch": 16,
                        "source": "profiles/r02_ncu_c1_many.txt (ncu --set full, one 16-step launch of pgm_fast_step_kernel<64,1,0,5>)"},
