@@ -1,4 +1,6 @@
-// pgm_kernels.cuh - the fused POGEMA step kernel for sm_100a.
+// pgm_kernels.cuh - the generic fused POGEMA step kernel for sm_100a: every shape GridConfig allows, the reset and
+// observe launches of every engine, and the step launches of the shapes the register-resident kernel of
+// pgm_fast.cuh does not cover (that kernel shares the helpers below and gives identical results).
 //
 // One TEAM of threads (a warp, or 64..1024 threads on a named barrier) owns one
 // instance for the whole launch; everything an instance needs lives in that
@@ -92,8 +94,7 @@ struct StepArgs {
   int teams_per_cta;
   int occ_tiles, occ_tiles_w, occ_tshift;  // OCC == 1: number of tiles (padded to 4), tiles per row, log2(tile side)
   // pgm_fast_step_kernel (pgm_fast.cuh) only
-  int off_stage;    // observation stream buffers (stage_bufs of stage_words 32-bit words each)
-  int stage_bufs, stage_words;
+  int off_stage;    // observation stream of one batch: TEAM agents, every warp owns its word-aligned piece
   int plane_words;  // block_both: words of one claim plane
   int narrow;       // map at most 32 cells wide and two bitmap words per row: one 64-bit load per observation row
 };

@@ -160,7 +160,7 @@ bool plan_fast(pgm_engine* e, int team, int want) {
   const int bitmap_bytes = round_up((e->PH * e->WPR + 1) * 4, 16);
   const bool bb = c.collision_system == PGM_COLLISION_BLOCK_BOTH;
   const int stage_one = round_up((team * e->stage_bpa + 31) / 32 * 4 + 16, 16);
-  auto build = [&](int bufs, StepArgs* L) {
+  auto build = [&](StepArgs* L) {
     int off = 0;
     L->off_obst = off;
     off += e->obst_stride * 4;
@@ -169,13 +169,13 @@ bool plan_fast(pgm_engine* e, int team, int want) {
     L->off_pbits = off;  // block_both: the second agent bitmap
     if (bb) off += bitmap_bytes;
     L->off_occ = off;
-    L->off_stage = off;  // block_both: the stream buffers lie over the claim planes (zeroed at the start of a step)
+    L->off_stage = off;  // block_both: the observation stream lies over the claim planes (zeroed at the start of a step)
     if (bb) {
-      off += std::max(2 * bitmap_bytes, bufs * stage_one);
+      off += std::max(2 * bitmap_bytes, stage_one);
     } else {
       off += round_up(e->PH * e->PW * 2, 16);
       L->off_stage = off;
-      off += bufs * stage_one;
+      off += stage_one;
     }
     L->off_link = off;
     if (!bb) off += round_up(apt * team * 4, 16);
@@ -184,8 +184,6 @@ bool plan_fast(pgm_engine* e, int team, int want) {
     L->off_misc = off;
     off += 16;
     L->team_smem = round_up(off, 16);
-    L->stage_bufs = bufs;
-    L->stage_words = stage_one / 4;
     L->plane_words = bitmap_bytes / 4;
     L->narrow = (e->WPR == 2 && c.width <= 32) ? 1 : 0;
     return L->team_smem;
@@ -193,7 +191,7 @@ bool plan_fast(pgm_engine* e, int team, int want) {
   auto fit = [](int team_smem) { return (228 * 1024) / (team_smem + 1024); };
   StepArgs L{};
   const int need = std::min(want, std::max(1, 1024 / team));
-  const int sm = build(1, &L);  // one stream buffer: every warp owns its piece of it (no double buffering needed)
+  const int sm = build(&L);
   if (sm > smem_max) return false;
   if (fit(sm) < std::min(need, 2) && want > 1) return false;  // the generic kernel's leaner layouts keep more instances resident
   e->f_layout = L;
@@ -310,8 +308,6 @@ int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
     f.off_misc = L.off_misc;
     f.team_smem = L.team_smem;
     f.teams_per_cta = L.teams_per_cta;
-    f.stage_bufs = L.stage_bufs;
-    f.stage_words = L.stage_words;
     f.plane_words = L.plane_words;
     f.narrow = L.narrow;
     d.team = e->f_team;
