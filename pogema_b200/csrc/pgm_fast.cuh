@@ -2,7 +2,7 @@
 //
 // Same step semantics and the same outputs, bit for bit, as pgm_step_kernel (pgm_kernels.cuh), for the shapes
 // the planner marks `fast` (pgm_plan.cu :: plan_fast): compile-time radius 2..7, at most 4 agents per thread
-// (APT), at most 8191 agents, uint8 / bit-packed observations, 16-byte aligned observation blocks.  What differs
+// (APT) of a team of up to 256 threads, uint8 / bit-packed observations.  What differs
 // is how the work is laid out - the generic kernel is bound by issue slots, not by HBM, on single-step launches
 // and on small radii (profiles/r01_single_step_instruction_mix.txt), so this one is written to issue less:
 //
@@ -117,24 +117,48 @@ __device__ __forceinline__ void fast_store_stream(uint32_t* stage, const uint32_
   }
 }
 
-// Expansion of `nbytes` stream bits (a multiple of 16, 16-byte aligned destination) into uint8 0/1: a lane turns
-// 16 stream bits into 16 bytes ((nibble * 0x00204081) & 0x01010101 per word) and issues one 16-byte streaming store;
-// a warp writes 512 contiguous bytes per instruction.  (A 256-entry shared-memory table byte -> 8 bytes halves the
-// instructions of this loop and was measured 10-30 % SLOWER: the two extra 64-bit loads per store bank-conflict.)
+// Expansion of `nbytes` stream bits into uint8 0/1 at `out`: a lane turns 16 stream bits into 16 bytes
+// ((nibble * 0x00204081) & 0x01010101 per word) and issues one 16-byte streaming store; a warp writes 512 contiguous
+// bytes per instruction.  (A 256-entry shared-memory table byte -> 8 bytes halves the instructions of this loop and
+// was measured 10-30 % SLOWER: the two extra 64-bit loads per store bank-conflict.)  `out` and `nbytes` are uniform
+// over the TEAM threads that call this.  Agent counts that are not a multiple of 16 make an instance's block start
+// off a 16-byte boundary: the chunks then start after `head` single bytes and read their 16 bits across two words.
 template <int TEAM>
 __device__ __forceinline__ void fast_expand_u8(const uint32_t* stage, uint8_t* out, int nbytes, int tid) {
-  const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
-  uint4* out16 = reinterpret_cast<uint4*>(out);
-  const int chunks = nbytes >> 4;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+  if (mis == 0u && (nbytes & 15) == 0) {
+    const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
+    uint4* out16 = reinterpret_cast<uint4*>(out);
+    const int chunks = nbytes >> 4;
 #pragma unroll 4
+    for (int c = tid; c < chunks; c += TEAM) {
+      const uint32_t v = st16[c];
+      uint4 o;
+      o.x = expand4(v & 15u);
+      o.y = expand4((v >> 4) & 15u);
+      o.z = expand4((v >> 8) & 15u);
+      o.w = expand4(v >> 12);
+      __stcs(out16 + c, o);
+    }
+    return;
+  }
+  const int head = min((int)((16u - mis) & 15u), nbytes);
+  const int chunks = (nbytes - head) >> 4;
+  uint4* out16 = reinterpret_cast<uint4*>(out + head);
   for (int c = tid; c < chunks; c += TEAM) {
-    const uint32_t v = st16[c];
+    const uint32_t bit = (uint32_t)head + ((uint32_t)c << 4);
+    const uint32_t v = __funnelshift_r(stage[bit >> 5], stage[(bit >> 5) + 1], bit & 31u);
     uint4 o;
     o.x = expand4(v & 15u);
     o.y = expand4((v >> 4) & 15u);
     o.z = expand4((v >> 8) & 15u);
-    o.w = expand4(v >> 12);
+    o.w = expand4((v >> 12) & 15u);
     __stcs(out16 + c, o);
+  }
+  const int tail0 = head + (chunks << 4);
+  for (int b = tid; b < head + (nbytes - tail0); b += TEAM) {
+    const int bb = b < head ? b : tail0 + (b - head);
+    out[bb] = (uint8_t)((stage[bb >> 5] >> (bb & 31)) & 1u);
   }
 }
 
