@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libpgm_b200.so")
+# PGM_B200_LIB: another build of the same library (A/B timing of two builds on one box); there is still no fallback
+LIB_PATH = os.environ.get("PGM_B200_LIB") or os.path.join(_HERE, "_lib", "libpgm_b200.so")
 
 PGM_ABI_VERSION = 1
 PGM_OK = 0

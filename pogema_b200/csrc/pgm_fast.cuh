@@ -121,31 +121,34 @@ __device__ __forceinline__ void fast_store_stream(uint32_t* stage, const uint32_
 // ((nibble * 0x00204081) & 0x01010101 per word) and issues one 16-byte streaming store; a warp writes 512 contiguous
 // bytes per instruction.  (A 256-entry shared-memory table byte -> 8 bytes halves the instructions of this loop and
 // was measured 10-30 % SLOWER: the two extra 64-bit loads per store bank-conflict.)  `out` and `nbytes` are uniform
-// over the TEAM threads that call this.  Agent counts that are not a multiple of 16 make an instance's block start
-// off a 16-byte boundary: the chunks then start after `head` single bytes and read their 16 bits across two words.
+// over the TEAM threads that call this.  This is the common case: `out` on a 16-byte boundary, `nbytes` a multiple of 16.
 template <int TEAM>
 __device__ __forceinline__ void fast_expand_u8(const uint32_t* stage, uint8_t* out, int nbytes, int tid) {
-  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
-  if (mis == 0u && (nbytes & 15) == 0) {
-    const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
-    uint4* out16 = reinterpret_cast<uint4*>(out);
-    const int chunks = nbytes >> 4;
+  const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
+  uint4* out16 = reinterpret_cast<uint4*>(out);
+  const int chunks = nbytes >> 4;
 #pragma unroll 4
-    for (int c = tid; c < chunks; c += TEAM) {
-      const uint32_t v = st16[c];
-      uint4 o;
-      o.x = expand4(v & 15u);
-      o.y = expand4((v >> 4) & 15u);
-      o.z = expand4((v >> 8) & 15u);
-      o.w = expand4(v >> 12);
-      __stcs(out16 + c, o);
-    }
-    return;
+  for (int c = tid; c < chunks; c += TEAM) {
+    const uint32_t v = st16[c];
+    uint4 o;
+    o.x = expand4(v & 15u);
+    o.y = expand4((v >> 4) & 15u);
+    o.z = expand4((v >> 8) & 15u);
+    o.w = expand4(v >> 12);
+    __stcs(out16 + c, o);
   }
+}
+
+// The same for a warp's piece that is off the 16-byte grid (agent counts that are not a multiple of 16 make an
+// instance's block start anywhere): `head` single bytes up to the next boundary, 16-byte chunks whose 16 bits
+// straddle two stream words, tail bytes.  Kept out of line: the step kernel calls it from every unrolled batch, and
+// inlining it there cost the large variants 6-10 % (instruction cache).
+static __device__ __noinline__ void fast_expand_u8_unaligned(const uint32_t* stage, uint8_t* out, int nbytes, int lane) {
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
   const int head = min((int)((16u - mis) & 15u), nbytes);
   const int chunks = (nbytes - head) >> 4;
   uint4* out16 = reinterpret_cast<uint4*>(out + head);
-  for (int c = tid; c < chunks; c += TEAM) {
+  for (int c = lane; c < chunks; c += 32) {
     const uint32_t bit = (uint32_t)head + ((uint32_t)c << 4);
     const uint32_t v = __funnelshift_r(stage[bit >> 5], stage[(bit >> 5) + 1], bit & 31u);
     uint4 o;
@@ -156,7 +159,7 @@ __device__ __forceinline__ void fast_expand_u8(const uint32_t* stage, uint8_t* o
     __stcs(out16 + c, o);
   }
   const int tail0 = head + (chunks << 4);
-  for (int b = tid; b < head + (nbytes - tail0); b += TEAM) {
+  for (int b = lane; b < head + (nbytes - tail0); b += 32) {
     const int bb = b < head ? b : tail0 + (b - head);
     out[bb] = (uint8_t)((stage[bb >> 5] >> (bb & 31)) & 1u);
   }
@@ -590,6 +593,8 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
       uint8_t* obs_n = obs_k + (long long)n * p.obs_inst_stride;
       const int warp = tid >> 5;
       uint32_t* wstage = s_stage + (uint32_t)warp * sbpa;  // this warp's sbpa words
+      // every piece of an instance starts a multiple of 32 bytes after the instance's block
+      const bool blocks_aligned = (reinterpret_cast<uintptr_t>(obs_n) & 15u) == 0u;
 #pragma unroll
       for (int q = 0; q < APT; ++q) {
         const int wfirst = q * TEAM + (warp << 5);          // first agent of this warp's piece
@@ -620,7 +625,9 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
           const int nw = (cnt * (int)sbpa + 31) >> 5;
           for (int w = lane; w < nw; w += 32) __stcs(out + w, wstage[w]);
         } else {
-          fast_expand_u8<32>(wstage, obs_n + (long long)wfirst * BPA, cnt * BPA, lane);
+          uint8_t* out = obs_n + (long long)wfirst * BPA;
+          if (blocks_aligned && cnt == 32) fast_expand_u8<32>(wstage, out, 32 * BPA, lane);
+          else fast_expand_u8_unaligned(wstage, out, cnt * BPA, lane);  // (also a last piece of 16 agents on the grid)
         }
         if (q == 0) PGM_STAMP(7);
       }

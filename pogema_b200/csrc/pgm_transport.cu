@@ -78,6 +78,9 @@ int ensure_stream(pgm_engine* e) {
     e->stream_unit_bytes = A * wpa * 4;
     e->stream_bytes = e->stream_unit_bytes * e->cfg.num_envs;
     CUDA_TRY(cudaMalloc((void**)&e->d_stream, (size_t)e->stream_bytes + 64));
+    // the stream of an instance is bit-contiguous and ends before its word-per-agent slot does: the gap is copied
+    // to the host with the rest (never read there); zero it once so that it is not uninitialised memory
+    CUDA_TRY(cudaMemset(e->d_stream, 0, (size_t)e->stream_bytes + 64));
     CUDA_TRY(cudaHostAlloc((void**)&e->h_stream, (size_t)e->stream_bytes + 64, cudaHostAllocDefault));
     memset(e->h_stream, 0, (size_t)e->stream_bytes + 64);
     if (const char* v = getenv("PGM_STREAM_CHUNKS")) e->stream_chunks = std::max(1, std::min(kMaxStreamChunks, atoi(v)));
