@@ -2,7 +2,7 @@
 //
 // Same step semantics and the same outputs, bit for bit, as pgm_step_kernel (pgm_kernels.cuh), for the shapes
 // the planner marks `fast` (pgm_plan.cu :: plan_fast): compile-time radius 2..7, at most 4 agents per thread
-// (APT) of a team of up to 256 threads, uint8 / bit-packed observations.  What differs
+// (APT), at most 8191 agents, uint8 / bit-packed observations, 16-byte aligned observation blocks.  What differs
 // is how the work is laid out - the generic kernel is bound by issue slots, not by HBM, on single-step launches
 // and on small radii (profiles/r01_single_step_instruction_mix.txt), so this one is written to issue less:
 //
@@ -117,11 +117,10 @@ __device__ __forceinline__ void fast_store_stream(uint32_t* stage, const uint32_
   }
 }
 
-// Expansion of `nbytes` stream bits into uint8 0/1 at `out`: a lane turns 16 stream bits into 16 bytes
-// ((nibble * 0x00204081) & 0x01010101 per word) and issues one 16-byte streaming store; a warp writes 512 contiguous
-// bytes per instruction.  (A 256-entry shared-memory table byte -> 8 bytes halves the instructions of this loop and
-// was measured 10-30 % SLOWER: the two extra 64-bit loads per store bank-conflict.)  `out` and `nbytes` are uniform
-// over the TEAM threads that call this.  This is the common case: `out` on a 16-byte boundary, `nbytes` a multiple of 16.
+// Expansion of `nbytes` stream bits (a multiple of 16, 16-byte aligned destination) into uint8 0/1: a lane turns
+// 16 stream bits into 16 bytes ((nibble * 0x00204081) & 0x01010101 per word) and issues one 16-byte streaming store;
+// a warp writes 512 contiguous bytes per instruction.  (A 256-entry shared-memory table byte -> 8 bytes halves the
+// instructions of this loop and was measured 10-30 % SLOWER: the two extra 64-bit loads per store bank-conflict.)
 template <int TEAM>
 __device__ __forceinline__ void fast_expand_u8(const uint32_t* stage, uint8_t* out, int nbytes, int tid) {
   const uint16_t* st16 = reinterpret_cast<const uint16_t*>(stage);
@@ -136,32 +135,6 @@ __device__ __forceinline__ void fast_expand_u8(const uint32_t* stage, uint8_t* o
     o.z = expand4((v >> 8) & 15u);
     o.w = expand4(v >> 12);
     __stcs(out16 + c, o);
-  }
-}
-
-// The same for a warp's piece that is off the 16-byte grid (agent counts that are not a multiple of 16 make an
-// instance's block start anywhere): `head` single bytes up to the next boundary, 16-byte chunks whose 16 bits
-// straddle two stream words, tail bytes.  Kept out of line: the step kernel calls it from every unrolled batch, and
-// inlining it there cost the large variants 6-10 % (instruction cache).
-static __device__ __noinline__ void fast_expand_u8_unaligned(const uint32_t* stage, uint8_t* out, int nbytes, int lane) {
-  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
-  const int head = min((int)((16u - mis) & 15u), nbytes);
-  const int chunks = (nbytes - head) >> 4;
-  uint4* out16 = reinterpret_cast<uint4*>(out + head);
-  for (int c = lane; c < chunks; c += 32) {
-    const uint32_t bit = (uint32_t)head + ((uint32_t)c << 4);
-    const uint32_t v = __funnelshift_r(stage[bit >> 5], stage[(bit >> 5) + 1], bit & 31u);
-    uint4 o;
-    o.x = expand4(v & 15u);
-    o.y = expand4((v >> 4) & 15u);
-    o.z = expand4((v >> 8) & 15u);
-    o.w = expand4((v >> 12) & 15u);
-    __stcs(out16 + c, o);
-  }
-  const int tail0 = head + (chunks << 4);
-  for (int b = lane; b < head + (nbytes - tail0); b += 32) {
-    const int bb = b < head ? b : tail0 + (b - head);
-    out[bb] = (uint8_t)((stage[bb >> 5] >> (bb & 31)) & 1u);
   }
 }
 
@@ -593,8 +566,6 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
       uint8_t* obs_n = obs_k + (long long)n * p.obs_inst_stride;
       const int warp = tid >> 5;
       uint32_t* wstage = s_stage + (uint32_t)warp * sbpa;  // this warp's sbpa words
-      // every piece of an instance starts a multiple of 32 bytes after the instance's block
-      const bool blocks_aligned = (reinterpret_cast<uintptr_t>(obs_n) & 15u) == 0u;
 #pragma unroll
       for (int q = 0; q < APT; ++q) {
         const int wfirst = q * TEAM + (warp << 5);          // first agent of this warp's piece
@@ -625,9 +596,7 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
           const int nw = (cnt * (int)sbpa + 31) >> 5;
           for (int w = lane; w < nw; w += 32) __stcs(out + w, wstage[w]);
         } else {
-          uint8_t* out = obs_n + (long long)wfirst * BPA;
-          if (blocks_aligned && cnt == 32) fast_expand_u8<32>(wstage, out, 32 * BPA, lane);
-          else fast_expand_u8_unaligned(wstage, out, cnt * BPA, lane);  // (also a last piece of 16 agents on the grid)
+          fast_expand_u8<32>(wstage, obs_n + (long long)wfirst * BPA, cnt * BPA, lane);
         }
         if (q == 0) PGM_STAMP(7);
       }

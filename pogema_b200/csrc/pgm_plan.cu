@@ -122,9 +122,9 @@ int choose_tpc(const pgm_engine* e, int team, int team_smem) {
   return tpc;
 }
 
-// The fast step kernel (pgm_fast.cuh) for the common shapes: compile-time radius 2..7, uint8 / bits observations,
-// at most 4 agents per thread of a team of up to 256 threads (1024 agents), both bitmaps (and for priority / soft
-// the uint16 cell grid) in shared memory at the residency the job wants.
+// The fast step kernel (pgm_fast.cuh) for the common shapes: compile-time radius 2..7, uint8 / bits observations
+// whose per-instance block is a multiple of 16 bytes, at most 4 agents per thread, at most 8190 agents, both bitmaps
+// (and for priority / soft the uint16 cell grid) in shared memory at the residency the job wants.
 bool plan_fast(pgm_engine* e, int team, int want) {
   const pgm_config& c = e->cfg;
   const int A = c.num_agents;
@@ -133,6 +133,7 @@ bool plan_fast(pgm_engine* e, int team, int want) {
   }
   if (c.obs_radius < 2 || c.obs_radius > 7) return false;
   if (c.obs_format != PGM_OBS_U8 && c.obs_format != PGM_OBS_BITS) return false;
+  if (c.obs_format == PGM_OBS_U8 && ((int64_t)A * e->bits_per_agent) % 16 != 0) return false;
   if (A > 8190 || e->obst_global) return false;
   // One agent per thread when a team of up to 256 threads can hold the instance: measured on a B200 with both launch
   // forms, 64 agents run 8-9 % faster on 64 threads than on 32 (16 steps per launch 17.0 -> 15.6 us, one launch per
@@ -290,8 +291,10 @@ int launch(pgm_engine* e, const StepArgs& a, int op, cudaStream_t s) {
   if (d.og && d.rt != 5) d.rt = 0;
   const int g = d.og ? (d.rt == 5 ? 1 : 0) : radius_group(d.rt);
   int err;
-  // step launches of the common shapes: the register-resident kernel
-  const bool fast = op == OP_STEP && e->fast;
+  // step launches of the common shapes: the register-resident kernel (uint8 observation blocks must be 16-byte aligned)
+  const bool fast = op == OP_STEP && e->fast &&
+                    (a.obs == nullptr || a.obs_format != 0 ||
+                     ((reinterpret_cast<uintptr_t>(a.obs) & 15u) == 0 && (a.obs_slot_stride & 15) == 0));
   if (fast) {
     StepArgs f = a;
     const StepArgs& L = e->f_layout;

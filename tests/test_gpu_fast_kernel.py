@@ -26,13 +26,10 @@ def build(gc, n, seeds, monkeypatch, fast, team=0, fast_team=None, fmt="u8", aut
 
 @pytest.mark.parametrize("coll", ["priority", "block_both", "soft"])
 @pytest.mark.parametrize("ot", ["finish", "nothing", "restart"])
-@pytest.mark.parametrize("fast_team,A", [(32, 32), (32, 64), (32, 128), (64, 64), (64, 208), (128, 256), (256, 1008), (128, 48),
-                                         (32, 5), (32, 20), (64, 100), (128, 250), (256, 1000)])  # (the last five: blocks off 16-byte boundaries)
+@pytest.mark.parametrize("fast_team,A", [(32, 32), (32, 64), (32, 128), (64, 64), (64, 208), (128, 256), (256, 1008), (128, 48)])
 def test_fast_equals_generic_and_oracle(coll, ot, fast_team, A, monkeypatch):
     import torch
     size = 20 if A <= 64 else (40 if A <= 256 else 72)
-    if A == 100:
-        size = 30
     gc = dict(size=size, density=0.15, num_agents=A, obs_radius=3 + (A % 3), max_episode_steps=9,
               collision_system=coll, on_target=ot)
     n = 5
@@ -116,16 +113,14 @@ def test_fast_kernel_behind_the_packed_host_transport(monkeypatch):
         assert np.array_equal(a.current_seeds(), b.current_seeds())
 
 
-def test_fast_kernel_handles_misaligned_observation_pointers(monkeypatch):
-    """uint8 observation pointers off a 16-byte boundary (a caller's view into a larger buffer): head / tail bytes
-    around the 16-byte chunks."""
+def test_fast_kernel_falls_back_on_misaligned_observation_pointers(monkeypatch):
     import torch
     gc = dict(size=16, density=0.2, num_agents=32, obs_radius=3, max_episode_steps=8)
     a = build(gc, 4, [1, 2, 3, 4], monkeypatch, True)
     b = build(gc, 4, [1, 2, 3, 4], monkeypatch, True)
     a.reset(), b.reset()
     raw = torch.empty(a.engine.obs_bytes + 64, dtype=torch.uint8, device="cuda")
-    odd = raw[3:3 + a.engine.obs_bytes].view(a.engine.obs_shape())      # 3 bytes off
+    odd = raw[3:3 + a.engine.obs_bytes].view(a.engine.obs_shape())      # 3 bytes off: generic kernel
     acts = make_actions(6, 4, 32, seed=2)
     for t in range(6):
         act = torch.from_numpy(acts[t]).cuda()
