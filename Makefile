@@ -31,12 +31,28 @@ $(LIB): $(OBJS)
 	@mkdir -p pogema_b200/_lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lpthread
 
+# Timeline build: the same library with the phase stamps compiled in (tools/phase_timeline.py loads it through
+# PGM_B200_LIB).  Not part of `all`: the product build carries no stamp code.
+TL_BUILD := build_tl
+TL_LIB := pogema_b200/_lib/libpgm_b200_timeline.so
+TL_OBJS := $(addprefix $(TL_BUILD)/,$(addsuffix .o,$(CU))) $(BUILD)/pgm_gen.o $(BUILD)/pgm_hostexpand.o
+
+$(TL_BUILD)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(TL_BUILD)
+	$(NVCC) $(NVFLAGS) -DPGM_TIMELINE -c $< -o $@
+
+$(TL_LIB): $(TL_OBJS)
+	@mkdir -p pogema_b200/_lib
+	$(NVCC) $(ARCH) -shared -o $@ $(TL_OBJS) -lpthread
+
+timeline: $(TL_LIB)
+
 oracle: oracle/liboracle_step.so
 
 oracle/liboracle_step.so: oracle/step_oracle.c
 	$(CC) -O2 -fPIC -shared -Wall -o $@ $< -lm
 
 clean:
-	rm -rf $(BUILD) $(LIB) oracle/liboracle_step.so
+	rm -rf $(BUILD) $(TL_BUILD) $(LIB) $(TL_LIB) oracle/liboracle_step.so
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean timeline

@@ -263,7 +263,9 @@ int pgm_checkpoint_load(pgm_engine* e, const void* src_host, int64_t src_bytes, 
 int pgm_check_errors(pgm_engine* e, void* stream);
 
 /* Development aid: if dev_ptr is not NULL every later launch stores clock64() stamps at its phase
- * boundaries into int64 [N][16] at dev_ptr (caller-owned device memory); NULL switches it off. */
+ * boundaries into int64 [N][16] at dev_ptr (caller-owned device memory); NULL switches it off.  The stamp code is
+ * compiled only into the timeline build of the library (`make timeline`, -DPGM_TIMELINE); in the product build the
+ * call is accepted and the kernels write nothing. */
 int pgm_set_debug_buffer(pgm_engine* e, void* dev_ptr);
 
 /* Number of kernel launches issued by this engine so far (bench `gpu_launches`). */

@@ -173,12 +173,14 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
   pdl_trigger();
   PGM_STAMP(0);
   PGM_STAMP_NS(9);
+#ifdef PGM_TIMELINE
   if (dbg != nullptr) {  // where this team runs: SM and hardware warp slot (tools/phase_timeline.py)
     uint32_t smid, warpid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
     dbg[12] = (long long)((smid << 16) | warpid);
   }
+#endif
   // ---- prologue (independent of the previous launch): the obstacle bitmap comes by bulk copy (TMA engine), the
   // team zeroes its agent bitmap and sets every cell of the grid to "nobody" with its own 16-byte stores.  (Filling
   // them by a second bulk copy from a constant template saves ~70 instructions per warp and was measured SLOWER on

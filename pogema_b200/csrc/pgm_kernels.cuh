@@ -350,6 +350,10 @@ __device__ __forceinline__ void agent_bits_static(const uint32_t* s_obst, const 
 // ------------------------------------------------------------------------- //
 // observation generation: batches of agents -> stage bit stream -> HBM
 // ------------------------------------------------------------------------- //
+// Phase stamps for tools/phase_timeline.py (pgm_set_debug_buffer).  They cost ~35 warp instructions per instance and
+// step even when no buffer is set, so they are compiled only into the timeline build of the library
+// (`make timeline` -> pogema_b200/_lib/libpgm_b200_timeline.so, -DPGM_TIMELINE; load it with PGM_B200_LIB).
+#ifdef PGM_TIMELINE
 #define PGM_STAMP(k)                        \
   do {                                      \
     if (dbg != nullptr) dbg[(k)] = clock64(); \
@@ -363,6 +367,10 @@ __device__ __forceinline__ void agent_bits_static(const uint32_t* s_obst, const 
       dbg[(k)] = (long long)_t;                                      \
     }                                                                \
   } while (0)
+#else
+#define PGM_STAMP(k) ((void)dbg)
+#define PGM_STAMP_NS(k) ((void)dbg)
+#endif
 
 template <int TEAM, int RT>
 __device__ __forceinline__ void emit_observations(const StepArgs& p, long long* dbg, uint8_t* obs, int n, int tid,

@@ -1,6 +1,13 @@
 """Per-phase cycle timeline of the step kernel (clock64 stamps, see pgm_set_debug_buffer)."""
 import argparse, sys, os, ctypes as C
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the stamps are compiled only into the timeline build of the library (`make timeline`)
+TL = os.path.join(ROOT, "pogema_b200", "_lib", "libpgm_b200_timeline.so")
+if not os.environ.get("PGM_B200_LIB"):
+    if not os.path.exists(TL):
+        sys.exit("tools/phase_timeline.py needs the timeline build of the library: run `make timeline` first")
+    os.environ["PGM_B200_LIB"] = TL
 import numpy as np, torch
 from pogema_b200 import BatchedPogema, GridConfig
 
