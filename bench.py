@@ -566,7 +566,9 @@ def run_cuda(args):
                         "steps_per_launch": SPL, "plan": plan_main},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000_GBps": achieved / 8000.0,
-                         "algorithmic_bytes_per_agent_step": bpa, "kernel": "pgm_step_kernel (pgm_step_many, up to %d steps per launch)" % SPL,
+                         "algorithmic_bytes_per_agent_step": bpa, "kernel": ("%s (pgm_step_many, up to %d steps per launch)" % (
+                             ("pgm_fast_step_kernel<%d,%d,...>" % (plan_main["fast"]["team_threads"], plan_main["fast"]["agents_per_thread"]))
+                             if plan_main.get("fast_step_kernel") else "pgm_step_kernel", SPL)),
                          "algorithmic_bytes_per_launch": N * A * bpa * (sizes[0] if sizes else 1),
                          "steady_state": {"frac": steady["roofline_frac"], "us_per_step": steady["us_per_step"], "steps": steady["steps"],
                                           "note": "same kernel over a longer window (16 steps per launch), for comparison with the K-step headline"}},
