@@ -15,7 +15,9 @@ Headline workload (BASELINE.json configs[1], the one the metric is quoted on):
 The K timed steps are issued as launches of pgm_step_many (a launch advances every instance by 16 steps -
 K <= 32: one launch of K steps - and writes every step's outputs); nothing else runs in the timed region.
 The same line carries, measured after the timed region:
-    closed_loop    one launch per step (pgm_step), CUDA graph replay - what an RL loop with a policy issues
+    closed_loop    one launch per step (pgm_step), CUDA graph replay - what an RL loop with a policy issues;
+                   closed_loop.groups: the same with the instances split into 2 / 4 groups on their own streams
+                   (double-buffered sampling: one group steps while the policy works on the other)
     configs        the other BASELINE.json configurations (configs[2], [3], [4] r=3/5/7 at this world size),
                    both launch forms, each against its own algorithmic bytes
     e2e            pgm_step_host with HOST buffers (copies inside the timed windows)
@@ -430,6 +432,53 @@ def run_cuda(args):
                                           "steps": reps * 16, "launch": "pgm_step, CUDA graph of 16 launches replayed"}
         return rec
 
+    def measure_groups(gcc, n_inst, n_agents, bpa, groups, target_ms=30.0):
+        """Closed loop over `groups` groups of instances (the double-buffered sampling of RL frameworks: the policy
+        works on one group's observations while the other groups step).  Every group is its own engine on its own
+        stream and advances with ONE LAUNCH PER STEP (CUDA graph of 16 single-step launches per group, replayed): a
+        group's step t+1 starts only after its own step t completed, but one group's dependent front (state loads,
+        move resolution, first bit assembly) overlaps the other groups' observation stores."""
+        n_g = n_inst // groups
+        hs = []
+        for k in range(groups):
+            st = torch.cuda.Stream(dev)
+            with torch.cuda.stream(st):
+                first = rank * n_inst + k * n_g
+                eg = BatchedPogema(gcc, num_envs=n_g, device=dev, seeds=np.arange(first, first + n_g, dtype=np.uint64), auto_reset=True)
+                eg.reset()
+                hg = Harness(torch, eg, dev, 4321 + 16 * rank + k)
+                hg.single_steps(0, 4)
+                hg.capture_graph(16)
+            hs.append(hg)
+        est_us = max(2.0, n_inst * n_agents * bpa / 5.0e12 * 1e6)
+        reps = int(min(128, max(3, target_ms * 1e3 / (est_us * 16))))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h.flush.fill_(1)  # (h.timed ran before: the buffer exists) L2 flushed, GPU busy while the CPU enqueues
+        e0.record(h.stream)
+        for hg in hs:
+            hg.stream.wait_event(e0)
+        for _ in range(reps):
+            for hg in hs:
+                with torch.cuda.stream(hg.stream):
+                    hg.graph.replay()
+        for hg in hs:
+            h.stream.wait_stream(hg.stream)
+        e1.record(h.stream)
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / (reps * 16)
+        plan_g = hs[0].env.engine.plan()
+        for hg in hs:
+            hg.env.check_errors()
+            hg.env.close()
+        del hs
+        torch.cuda.empty_cache()
+        return {"groups": groups, "instances_per_group": n_g, "us_per_step": ms * 1e3,
+                "agent_steps_per_s": world * n_g * groups * n_agents / (ms * 1e-3),
+                "roofline_frac": n_g * groups * n_agents * bpa / (ms * 1e-3) / 1e9 / peak, "steps_per_group": reps * 16,
+                "launch": "pgm_step, one launch per step and group; %d engines on %d streams, CUDA graph of 16 launches each" % (groups, groups),
+                "plan": plan_g.get("fast", plan_g)}
+
     r = WORKLOAD["obs_radius"]
     P = WORKLOAD["size"] + 2 * r
     bpa = algorithmic_bytes_per_agent_step(r, A, P)
@@ -440,6 +489,8 @@ def run_cuda(args):
         closed_loop = {"value": cl["agent_steps_per_s"], "unit": UNIT, "ms_per_step": cl["us_per_step"] * 1e-3,
                        "steps": cl["steps"], "roofline_frac": cl["roofline_frac"],
                        "launch": "one kernel launch per step (pgm_step), CUDA graph of 16 launches replayed"}
+        if not args.no_configs:
+            closed_loop["groups"] = [measure_groups(gc, N, A, bpa, g) for g in (2, 4)]
     steady = forms["steps_per_launch_16"]
     plan_main = env.engine.plan()
 
@@ -470,6 +521,8 @@ def run_cuda(args):
             rec = {"config": name, "instances_per_gpu": n_inst, "agents_per_instance": aa, "scaling": scaling,
                    "algorithmic_bytes_per_agent_step": b, "plan": e2.engine.plan(), "obs_ring_slots": h2.nring}
             rec.update(measure_forms(h2, n_inst, aa, b))
+            if not args.no_graph and name.startswith("configs[2]"):
+                rec["one_launch_per_step_2_groups"] = measure_groups(gcc, n_inst, aa, b, 2)
             e2.check_errors()
             config_records.append(rec)
             e2.close()

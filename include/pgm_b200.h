@@ -73,8 +73,13 @@ enum {
                                   avg_throughput = [0]/max_episode_steps)
                               [1] sum of per-agent solve steps         (ep_length = [1]/A + 1)
                               [2] episode length in steps  [3] agents on goal at the last step     */
-  PGM_STATE_SEEDS = 8      /* uint64 [N] seed each instance's current task was built from (advances
+  PGM_STATE_SEEDS = 8,     /* uint64 [N] seed each instance's current task was built from (advances
                               under auto_reset=2)                                                  */
+  PGM_STATE_SOLVE_COSTS = 9 /* int32 [N][A], on_target = nothing only: per-agent cost of the last finished
+                              episode as upstream wrappers/metrics.py :: SumOfCostsAndMakespanMetric counts
+                              it - the step at which the agent's final stay on its goal began, or the last
+                              step (SoC = sum + A, makespan = max + 1).  pgm_state_ptr: the raw
+                              int32 [N][A][2] array (running start of the stay | that cost)        */
 };
 
 typedef struct pgm_config {

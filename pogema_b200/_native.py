@@ -18,7 +18,7 @@ PGM_ERR_INVALID, PGM_ERR_CUDA, PGM_ERR_UNSUPPORTED, PGM_ERR_OVERFLOW, PGM_ERR_ST
 COLLISION = {"priority": 0, "block_both": 1, "soft": 2}
 ON_TARGET = {"finish": 0, "nothing": 1, "restart": 2}
 OBS_FORMAT = {"u8": 0, "bits": 1, "f32": 2, "f16": 3}
-STATE_POSITIONS, STATE_TARGETS, STATE_ACTIVE, STATE_ELAPSED, STATE_OBSTACLES, STATE_WAS_ON_GOAL, STATE_EPISODE_DONE, STATE_METRICS, STATE_SEEDS = range(9)
+STATE_POSITIONS, STATE_TARGETS, STATE_ACTIVE, STATE_ELAPSED, STATE_OBSTACLES, STATE_WAS_ON_GOAL, STATE_EPISODE_DONE, STATE_METRICS, STATE_SEEDS, STATE_SOLVE_COSTS = range(10)
 
 # every symbol include/pgm_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [

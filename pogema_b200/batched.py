@@ -82,6 +82,35 @@ class BatchedPogema:
             self._truncated = torch.empty((n, a), dtype=torch.bool, device=self.device)
         self.obs_shape = tuple(self._obs.shape[1:])
 
+    @classmethod
+    def groups(cls, grid_config: Optional[GridConfig], num_envs: int, groups: int = 2, device="cuda",
+               seeds: Optional[Sequence[int]] = None, **kwargs):
+        """``groups`` envs over contiguous shares of ``num_envs`` instances, each with its own CUDA stream:
+        ``[(env, stream), ...]``.  For closed loops (a policy between steps): step group 0 on its stream while the
+        policy works on group 1's observations and vice versa (the double-buffered sampling of RL frameworks).  A
+        single env's one-launch-per-step form leaves HBM idle during the dependent front of every step (state loads,
+        move resolution, first bit assembly: 0.85 of the roofline on configs[1]); with two groups one group's front
+        overlaps the other's observation stores (0.96, four groups 0.99 - ``closed_loop.groups`` in the bench line).
+        Instance k of the job keeps seed ``seeds[k]``, so the results do not depend on the number of groups."""
+        if grid_config is None:
+            grid_config = GridConfig(**{k: kwargs.pop(k) for k in list(kwargs) if k in GridConfig.model_fields})
+        elif isinstance(grid_config, dict):
+            grid_config = GridConfig(**grid_config)
+        if num_envs % groups != 0:
+            raise ValueError("num_envs must be a multiple of groups")
+        if seeds is None:
+            base = grid_config.seed or 0
+            seeds = np.arange(base, base + num_envs, dtype=np.uint64)
+        seeds = np.asarray(seeds, dtype=np.uint64)
+        dev = torch.device(device)
+        n_g = num_envs // groups
+        out = []
+        for k in range(groups):
+            st = torch.cuda.Stream(dev)
+            with torch.cuda.stream(st):
+                out.append((cls(grid_config, n_g, device=device, seeds=seeds[k * n_g:(k + 1) * n_g], **kwargs), st))
+        return out
+
     # ------------------------------------------------------------------ #
     def _stream(self) -> int:
         return int(torch.cuda.current_stream(self.device).cuda_stream)
@@ -225,7 +254,12 @@ class BatchedPogema:
         if ot == 'restart':
             return {"avg_throughput": raw[:, 0] / self.grid_config.max_episode_steps}
         if ot == 'nothing':
-            return {"ISR": raw[:, 3] / a, "CSR": (raw[:, 3] == a).astype(np.float64), "ep_length": raw[:, 2]}
+            # SoC / makespan: upstream wrappers/metrics.py :: SumOfCostsAndMakespanMetric (per-agent costs latched by
+            # the step kernel at the end of the episode; zeros until an instance has finished one)
+            cost = self.engine.get_state(nat.STATE_SOLVE_COSTS, self._stream()).astype(np.float64)
+            fin = raw[:, 2] > 0
+            return {"ISR": raw[:, 3] / a, "CSR": (raw[:, 3] == a).astype(np.float64), "ep_length": raw[:, 2],
+                    "SoC": np.where(fin, cost.sum(axis=1) + a, 0.0), "makespan": np.where(fin, cost.max(axis=1) + 1, 0.0)}
         return {"ISR": raw[:, 0] / a, "CSR": (raw[:, 0] == a).astype(np.float64), "ep_length": raw[:, 1] / a + 1}
 
     # -- checkpoint / resume ------------------------------------------------ #

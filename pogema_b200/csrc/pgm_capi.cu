@@ -43,6 +43,7 @@ int upload_instances(pgm_engine* e, int first, int count, std::vector<GenInstanc
   CUDA_TRY(cudaMemsetAsync(e->d_elapsed + first, 0, (size_t)count * 4, s));
   CUDA_TRY(cudaMemsetAsync(e->d_macc + (size_t)first * 4, 0, (size_t)count * 16, s));
   CUDA_TRY(cudaMemsetAsync(e->d_mlast + (size_t)first * 4, 0, (size_t)count * 16, s));
+  if (e->d_solve) CUDA_TRY(cudaMemsetAsync(e->d_solve + (size_t)first * A * 2, 0, (size_t)count * A * 8, s));
   std::vector<Pcg64> rng;
   std::vector<int32_t> cstart, csize;
   std::vector<uint32_t> cells;
@@ -148,6 +149,7 @@ DevGenArgs devgen_args(pgm_engine* e, double density, bool has_map) {
   a.was_on_goal = e->d_was;
   a.metric_acc = e->d_macc;
   a.metric_last = e->d_mlast;
+  a.solve = e->d_solve;
   a.rng = e->d_rng;
   a.rng0 = e->d_rng0;
   a.comp_start = e->d_cstart;
@@ -275,6 +277,7 @@ int pgm_create(const pgm_config* cfg, pgm_engine** out) {
   TRY_ALLOC(dev_alloc(&e->d_elapsed, (size_t)N));
   TRY_ALLOC(dev_alloc(&e->d_macc, (size_t)N * 4));
   TRY_ALLOC(dev_alloc(&e->d_mlast, (size_t)N * 4));
+  if (e->cfg.on_target == 1) TRY_ALLOC(dev_alloc(&e->d_solve, (size_t)N * A * 2));
   TRY_ALLOC(dev_alloc(&e->d_err, 1));
   TRY_ALLOC(dev_alloc(&e->d_cur_seeds, (size_t)N));
   TRY_ALLOC(dev_alloc(&e->d_regen_flag, (size_t)N));
@@ -298,7 +301,7 @@ int pgm_destroy(pgm_engine* e) {
   void* ptrs[] = {e->d_obst,  e->d_state, e->d_state0, e->d_was,
                   e->d_done,  e->d_elapsed, e->d_macc, e->d_mlast,  e->d_rng,   e->d_rng0,   e->d_cstart,
                   e->d_csize, e->d_cells, e->d_err,   e->d_act_h,  e->d_obs_h /* base of the result block */,
-                  e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count};
+                  e->d_gen_seeds, e->d_gen_fail, e->d_gen_index, e->d_gen_map, e->d_gen_scratch, e->d_cur_seeds, e->d_regen_flag, e->d_regen_count, e->d_solve};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   free_transport(e);
@@ -592,6 +595,16 @@ int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, voi
       CUDA_TRY(cudaStreamSynchronize(s));
       return PGM_OK;
     }
+    case PGM_STATE_SOLVE_COSTS: {
+      if (!e->d_solve) return fail(PGM_ERR_INVALID, "solve costs exist only with on_target = nothing");
+      if (need(N * A * 4)) return PGM_ERR_INVALID;
+      std::vector<int32_t> tmp((size_t)(N * A * 2));
+      CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->d_solve, tmp.size() * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      int32_t* o = (int32_t*)dst;
+      for (int64_t i = 0; i < N * A; ++i) o[i] = tmp[2 * i + 1];
+      return PGM_OK;
+    }
     case PGM_STATE_SEEDS: {
       if (need(N * 8)) return PGM_ERR_INVALID;
       CUDA_TRY(cudaMemcpyAsync(dst, e->d_cur_seeds, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
@@ -629,6 +642,7 @@ void* pgm_state_ptr(pgm_engine* e, int32_t what) {
     case PGM_STATE_WAS_ON_GOAL: return e->d_was;
     case PGM_STATE_EPISODE_DONE: return e->d_done;
     case PGM_STATE_METRICS: return e->d_mlast;
+    case PGM_STATE_SOLVE_COSTS: return e->d_solve;
     default: return nullptr;
   }
 }
@@ -671,6 +685,7 @@ std::vector<CkptPart> ckpt_parts(const pgm_engine* e) {
   std::vector<CkptPart> v = {{e->d_state, N * A * 8}, {e->d_was, N * A},   {e->d_elapsed, N * 4},  {e->d_done, N},
                              {e->d_macc, N * 16},     {e->d_mlast, N * 16}, {e->d_cur_seeds, N * 8}};
   if (e->lifelong) v.push_back({e->d_rng, N * A * sizeof(Pcg64)});
+  if (e->d_solve) v.push_back({e->d_solve, N * A * 8});
   if (e->cfg.auto_reset == 2) {
     v.push_back({e->d_obst, N * (size_t)e->obst_stride * 4});
     v.push_back({e->d_state0, N * A * 8});

@@ -33,6 +33,7 @@ struct DevGenArgs {
   uint8_t* was_on_goal;
   int32_t* metric_acc;
   int32_t* metric_last;
+  int32_t* solve;  // null unless on_target == nothing (pgm_kernels.cuh :: StepArgs::solve)
   Pcg64* rng;
   Pcg64* rng0;
   int32_t* comp_start;

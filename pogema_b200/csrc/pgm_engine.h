@@ -75,6 +75,7 @@ struct pgm_engine {
   uint2 *d_state = nullptr, *d_state0 = nullptr;  // see pgm_kernels.cuh: x | active<<15 | y<<16 , target
   uint8_t *d_was = nullptr, *d_done = nullptr;
   int32_t *d_elapsed = nullptr, *d_macc = nullptr, *d_mlast = nullptr;
+  int32_t* d_solve = nullptr;  // [N][A][2], on_target == nothing only (StepArgs::solve)
   pgm::Pcg64 *d_rng = nullptr, *d_rng0 = nullptr;
   int32_t *d_cstart = nullptr, *d_csize = nullptr;
   uint32_t* d_cells = nullptr;

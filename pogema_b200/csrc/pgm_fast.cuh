@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
       trunc_ptr[q * TEAM] = trunc ? 1 : 0;
       p.was_on_goal[ia + a] = was[q] ? 1 : 0;
       uint32_t pp = npos[q];
+      if (ONTGT == 1) solve_time_update(p.solve + 2 * (ia + a), was[q], pp != pos[q], pos[q] == tt, done, m_acc2);
       if (do_reset) {
         const uint2 w = p.state0[ia + a];
         pp = st_pos(w.x);

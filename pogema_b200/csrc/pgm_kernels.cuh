@@ -70,6 +70,9 @@ struct StepArgs {
   uint8_t* episode_done;
   int32_t* metric_acc;   // [N][4] running: solved, time_sum, cur_step, unused
   int32_t* metric_last;  // [N][4] latched at episode end: solved, time_sum, steps, on_goal_now
+  int32_t* solve;        // on_target == nothing only, [N][A][2]: step at which the agent's current stay on its goal
+                         // began | its cost in the last finished episode (SumOfCostsAndMakespanMetric); touched
+                         // only when an agent arrives and when an episode ends
   // io
   const uint8_t* actions;
   int act_itemsize;
@@ -178,6 +181,21 @@ __device__ __forceinline__ uint32_t load_action(const uint8_t* base, long long i
 
 __device__ __forceinline__ int opposite(int a) { return a == 0 ? 0 : (((a - 1) ^ 1) + 1); }  // 1<->2, 3<->4
 __device__ __forceinline__ int move_dx(int a) { return a == 1 ? -1 : (a == 2 ? 1 : 0); }
+
+// upstream wrappers/metrics.py :: SumOfCostsAndMakespanMetric (on_target == nothing), per agent and step:
+//   solve_time is None and (on_goal or finished) -> solve_time = step;   not on_goal and not finished -> None;
+//   finished -> cost = solve_time.
+// sv[0] holds the step at which the current stay on the goal began (0 after a reset: an agent standing on its goal
+// without having arrived has been there since the reset); global memory is touched only on an arrival and at the end
+// of an episode.  An agent that steps off its goal on the finishing step keeps the stay's start (upstream's rule).
+__device__ __forceinline__ void solve_time_update(int32_t* sv, bool was, bool moved, bool was_before, bool done, int step) {
+  const bool arrived = was && moved;
+  if (arrived) sv[0] = step;
+  if (done) {
+    sv[1] = arrived ? step : ((was || was_before) ? sv[0] : step);
+    sv[0] = 0;
+  }
+}
 __device__ __forceinline__ int move_dy(int a) { return a == 3 ? -1 : (a == 4 ? 1 : 0); }
 
 __device__ __forceinline__ uint32_t bit_at(const uint32_t* bits, int WPR, int x, int y) {
@@ -835,6 +853,7 @@ __global__ void __launch_bounds__(1024, 1)
         p.truncated[oa + a] = trunc ? 1 : 0;
         p.was_on_goal[ia + a] = (uint8_t)was;
         uint32_t pp = s_npos[a];
+        if (ONTGT == 1) solve_time_update(p.solve + 2 * (ia + a), was != 0u, pp != s_pos[a], s_pos[a] == tt, done, m_acc2);
         if (do_reset) {
           const uint2 w = p.state0[ia + a];
           pp = st_pos(w.x);
@@ -880,6 +899,7 @@ __global__ void __launch_bounds__(1024, 1)
         p.state[ia + a] = make_uint2(s_pos[a] | 0x8000u, s_tgt[a]);
         p.was_on_goal[ia + a] = (s_pos[a] == s_tgt[a]) ? 1 : 0;
         if (ONTGT == 2) p.rng[ia + a] = p.rng0[ia + a];
+        if (ONTGT == 1) p.solve[2 * (ia + a)] = 0;
       }
       if (tid == 0) {
         p.elapsed[n] = 0;

@@ -372,6 +372,7 @@ StepArgs make_args(pgm_engine* e) {
   a.episode_done = e->d_done;
   a.metric_acc = e->d_macc;
   a.metric_last = e->d_mlast;
+  a.solve = e->d_solve;
   a.actions = nullptr;
   a.act_itemsize = 1;
   a.num_steps = 1;

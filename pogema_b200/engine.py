@@ -179,6 +179,7 @@ class Engine:
             nat.STATE_OBSTACLES: ((n, self.height, self.width), np.uint8),
             nat.STATE_WAS_ON_GOAL: ((n, a), np.uint8), nat.STATE_EPISODE_DONE: ((n,), np.uint8),
             nat.STATE_METRICS: ((n, 4), np.int32), nat.STATE_SEEDS: ((n,), np.uint64),
+            nat.STATE_SOLVE_COSTS: ((n, a), np.int32),
         }
         shape, dtype = shapes[what]
         out = np.empty(shape, dtype=dtype)

@@ -310,7 +310,9 @@ class PogemaBase(_Base):
         if ot == 'restart':
             return {'avg_throughput': int(raw[0]) / self.grid_config.max_episode_steps}
         if ot == 'nothing':
-            return {'ISR': float(int(raw[3])) / n, 'CSR': float(int(raw[3]) == n), 'ep_length': int(raw[2])}
+            cost = self._engine.get_state(nat.STATE_SOLVE_COSTS)[0]  # upstream SumOfCostsAndMakespanMetric
+            return {'ISR': float(int(raw[3])) / n, 'CSR': float(int(raw[3]) == n), 'ep_length': int(raw[2]),
+                    'SoC': int(cost.sum()) + n, 'makespan': int(cost.max()) + 1}
         return {'ISR': int(raw[0]) / n, 'CSR': float(int(raw[0]) == n), 'ep_length': int(raw[1]) / n + 1}
 
     def sample_actions(self):

@@ -8,6 +8,7 @@ step (``pgm_checkpoint_save`` / ``pgm_checkpoint_load``)."""
 from __future__ import annotations
 
 import os
+import time
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -313,6 +314,36 @@ class AnimationMonitor(_Wrapper):
         with open(name, 'w') as f:
             f.write(svg)
         return name
+
+
+class RuntimeMetricWrapper(_Wrapper):
+    """upstream wrappers/metrics.py :: RuntimeMetricWrapper (opt-in upstream too): ``metrics['runtime']`` = wall-clock
+    seconds of the episode spent outside ``env.step``, i.e. the policy's time."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self._start_time = None
+        self._env_step_time = 0.0
+
+    def reset(self, **kwargs):
+        out = self.env.reset(**kwargs)
+        self._start_time = time.monotonic()
+        self._env_step_time = 0.0
+        return out
+
+    def step(self, action):
+        t0 = time.monotonic()
+        obs, rewards, terminated, truncated, infos = self.env.step(action)
+        t1 = time.monotonic()
+        self._env_step_time += t1 - t0
+        if all(terminated) or all(truncated):
+            if self._start_time is None:  # stepped without a reset through this wrapper
+                self._start_time = t0
+            infos[0].setdefault('metrics', {})['runtime'] = time.monotonic() - self._start_time - self._env_step_time
+            if getattr(self.env.unwrapped.grid_config, 'auto_reset', None):  # the inner env already started a new episode
+                self._start_time = time.monotonic()
+                self._env_step_time = 0.0
+        return obs, rewards, terminated, truncated, infos
 
 
 class AutoResetWrapper(_Wrapper):

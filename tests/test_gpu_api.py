@@ -437,3 +437,39 @@ def test_env_classes_fix_their_on_target_semantics():
         ro, rr, rte, rtr, _ = ref.step(a)
         assert list(r) == list(rr) and list(te) == list(rte) and list(tr) == list(rtr)
         assert all(np.array_equal(x, y) for x, y in zip(o, ro))
+
+
+def test_groups_on_their_own_streams_equal_one_env():
+    """BatchedPogema.groups: G envs over contiguous shares of the instances, each stepping on its own stream
+    (interleaved, as a closed loop with double-buffered sampling would) == one env over all instances."""
+    import torch
+    from pogema_b200 import BatchedPogema, GridConfig
+    kw = dict(size=16, density=0.2, num_agents=32, obs_radius=4, max_episode_steps=9, collision_system="soft",
+              on_target="restart")
+    n, G = 12, 3
+    one = BatchedPogema(GridConfig(**kw), num_envs=n, auto_reset=True)
+    parts = BatchedPogema.groups(GridConfig(**kw), n, groups=G, auto_reset=True)
+    assert len(parts) == G and len({st.cuda_stream for _, st in parts}) == G
+    ref = one.reset().clone()
+    got = []
+    for env, st in parts:
+        with torch.cuda.stream(st):
+            got.append(env.reset().clone())
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(got), ref)
+    rng = np.random.default_rng(4)
+    for t in range(25):
+        acts = torch.from_numpy(rng.integers(0, 5, size=(n, 32)).astype(np.uint8)).cuda()
+        want = [x.clone() for x in one.step(acts)]
+        torch.cuda.synchronize()
+        outs = []
+        for k, (env, st) in enumerate(parts):
+            with torch.cuda.stream(st):
+                outs.append([x.clone() for x in env.step(acts[k * (n // G):(k + 1) * (n // G)])])
+        torch.cuda.synchronize()
+        for j in range(4):
+            assert torch.equal(torch.cat([o[j] for o in outs]), want[j]), (t, j)
+    for env, _ in parts:
+        env.check_errors()
+    with pytest.raises(ValueError):
+        BatchedPogema.groups(GridConfig(**kw), 10, groups=3)

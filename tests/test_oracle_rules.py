@@ -79,7 +79,21 @@ def test_time_limit_and_metrics():
     assert rew == [0.0, 0.0] and term == [False, False]
     _, rew, term, _, info = env.step([0, 4])
     assert rew == [1.0, 1.0] and term == [True, True]
-    assert info[0]["metrics"] == {"ISR": 1.0, "CSR": 1.0, "ep_length": 2}
+    # SumOfCostsAndMakespanMetric: a has stood on its goal since step 0, b since step 1 -> SoC = 0 + 1 + 2 agents
+    assert info[0]["metrics"] == {"ISR": 1.0, "CSR": 1.0, "ep_length": 2, "SoC": 3, "makespan": 2}
+
+
+def test_sum_of_costs_counts_the_final_stay():
+    """a arrives, overshoots, returns at step 2; b stands on its goal from step 0 and steps off on the finishing step
+    (upstream keeps the start of that stay); c never arrives and costs the last step."""
+    gc = orc.GridConfig(map="aA..\nbB..\nc..C", obs_radius=2, on_target="nothing", max_episode_steps=5, seed=0)
+    env = orc.pogema_v0(gc)
+    env.reset()
+    for acts in ([4, 4, 0], [4, 0, 0], [3, 0, 0], [0, 0, 0], [0, 4, 0]):
+        _, _, term, trunc, info = env.step(acts)
+    assert trunc == [True] * 3 and term == [False] * 3
+    assert info[0]["metrics"]["SoC"] == (2 + 0 + 4) + 3 and info[0]["metrics"]["makespan"] == 5
+    assert info[0]["metrics"]["ISR"] == 1 / 3
 
 
 def test_lifelong_new_target_comes_from_the_agents_generator():
