@@ -24,6 +24,15 @@ python tools/phase_timeline.py > $O/r02_timeline_c1.txt 2>&1
 python tools/phase_timeline.py --n 2048 --r 3 > $O/r02_timeline_r3.txt 2>&1
 python tools/phase_timeline.py --n 512 --size 256 --agents 1024 --coll block_both --map warehouse > $O/r02_timeline_c3.txt 2>&1
 python tools/bench_configs.py > $O/r02_configs.json 2> $O/r02_configs.err
+# steps per launch: 8 / 16 / 32 / 64 on configs[1] and configs[2] (do the per-team timelines drift apart in long launches?)
+( for k in 8 16 32 64; do python tools/quick_bench.py --steps 2048 --many $k; done
+  for k in 8 16 32 64; do python tools/quick_bench.py --n 1024 --size 64 --agents 256 --coll soft --ot restart --map maze --steps 1024 --many $k; done ) > $O/r02_spl_sweep.jsonl 2>&1
+# closed loop over G groups of instances on their own streams (BatchedPogema.groups): every BASELINE configuration
+( for g in 1 2 4; do python tools/two_groups.py --groups $g; done
+  for g in 1 2 4; do python tools/two_groups.py --groups $g --n 1024 --size 64 --agents 256 --coll soft --ot restart --map maze --steps 512; done
+  for g in 1 2; do python tools/two_groups.py --groups $g --n 512 --size 256 --agents 1024 --coll block_both --map warehouse --steps 256; done
+  for g in 1 2; do python tools/two_groups.py --groups $g --n 2048 --r 3 --steps 1024; done
+  for g in 1 2 4; do python tools/two_groups.py --groups $g --n 16384 --r 3 --steps 256; done ) > $O/r02_groups.jsonl 2> $O/r02_groups.err
 bash tools/gpu/r02_b_san.sh > $O/r02_sanitizer_fast.log 2>&1
 bash tools/sanitize.sh > $O/r02_sanitizer_generic.log 2>&1
 # summarise the captures HERE (gpurun brings back at most 64 MiB): text summaries stay, of the reports only configs[1]'s

@@ -34,7 +34,8 @@ for f in sorted(glob.glob(f"{G}/r02_ncu_*.txt")):
                       open(f"{P}/traffic.json", "w"), indent=1)
 for a, b in [("r02_bench.json", "r02_bench.json"), ("r02_bench_driver.json", "r02_bench_driver.json"), ("r02_bench_reference.json", "r02_bench_reference.json"),
              ("r02_timeline_c1.txt", "r02_phase_timeline_c1.txt"), ("r02_timeline_r3.txt", "r02_phase_timeline_r3.txt"),
-             ("r02_timeline_c3.txt", "r02_phase_timeline_c3.txt"), ("r02_configs.json", "r02_configs.json")]:
+             ("r02_timeline_c3.txt", "r02_phase_timeline_c3.txt"), ("r02_configs.json", "r02_configs.json"),
+             ("r02_groups.jsonl", "r02_groups.jsonl"), ("r02_spl_sweep.jsonl", "r02_spl_sweep.jsonl")]:
     if os.path.exists(f"{G}/{a}"): shutil.copy(f"{G}/{a}", f"{P}/{b}")
 san = []
 for f in ("r02_sanitizer_fast.log", "r02_sanitizer_generic.log"):
