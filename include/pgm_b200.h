@@ -197,9 +197,6 @@ int pgm_step(pgm_engine* e, const void* actions_dev, int32_t action_itemsize, vo
  * memory, the observation stores of one instance overlap the move phases of the others.
  *   actions_dev:  [K][N][A]        rewards/terminated/truncated_dev: [K][N][A]
  *   obs_dev:      [obs_ring][N][A]... step k writes slot k % obs_ring (NULL skips observations)
- * More than 24 steps go out as back-to-back launches of at most 16 steps each (the per-instance
- * timelines of one launch drift apart, and long launches run ~5 % slower per step); the results
- * and the layout of the outputs do not depend on that.
  */
 int pgm_step_many(pgm_engine* e, int32_t num_steps, const void* actions_dev, int32_t action_itemsize,
                   void* obs_dev, int32_t obs_ring, float* rewards_dev, uint8_t* terminated_dev,

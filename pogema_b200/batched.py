@@ -174,8 +174,7 @@ class BatchedPogema:
         return obs.numpy(), rew.numpy(), term.numpy().astype(bool), trunc.numpy().astype(bool)
 
     def rollout(self, actions: torch.Tensor, obs_out: Optional[torch.Tensor] = None, compute_obs: bool = True):
-        """K consecutive steps without returning to the host (``pgm_step_many``: one kernel launch for up to 24 steps,
-        back-to-back launches of at most 16 steps beyond that) for actions known in advance.
+        """K consecutive steps in ONE kernel launch (``pgm_step_many``) for actions known in advance.
 
         actions: int tensor [K, N, A].  Returns (obs [R, N, A, ...], rewards [K, N, A], terminated [K, N, A],
         truncated [K, N, A]); step k writes observation slot ``k % R`` where R = ``obs_out.shape[0]`` (default:

@@ -531,32 +531,18 @@ int pgm_step_many(pgm_engine* e, int32_t num_steps, const void* actions_dev, int
   DeviceGuard guard(e->cfg.device);
   const long long NA = (long long)e->cfg.num_envs * e->cfg.num_agents;
   StepArgs a = make_args(e);
+  a.actions = (const uint8_t*)actions_dev;
   a.act_itemsize = action_itemsize;
+  a.num_steps = num_steps;
   a.act_step_stride = NA * action_itemsize;
   a.out_step_stride = NA;
   a.obs = (uint8_t*)obs_dev;
   a.obs_ring = obs_dev ? obs_ring : 1;
   a.obs_slot_stride = e->obs_bytes;
-  // Inside a launch every instance runs its own timeline and the timelines drift apart: launches of 32 / 64 steps
-  // run ~5 % slower per step than launches of 8 - 16 (profiles/r02_spl_sweep.jsonl).  A long rollout therefore goes
-  // out as back-to-back launches of at most kMaxStepsPerLaunch steps (programmatic dependent launch hides the seams);
-  // up to 24 steps stay one launch (one ramp, one tail).
-  constexpr int kMaxStepsPerLaunch = 16, kOneLaunchUpTo = 24;
-  const int launches = num_steps <= kOneLaunchUpTo ? 1 : (num_steps + kMaxStepsPerLaunch - 1) / kMaxStepsPerLaunch;
-  int k0 = 0;
-  for (int l = 0; l < launches; ++l) {
-    const int k = num_steps / launches + (l < num_steps % launches ? 1 : 0);
-    a.actions = (const uint8_t*)actions_dev + (long long)k0 * a.act_step_stride;
-    a.num_steps = k;
-    a.obs_slot0 = obs_dev ? k0 % obs_ring : 0;
-    a.rewards = rewards_dev + (long long)k0 * NA;
-    a.terminated = terminated_dev + (long long)k0 * NA;
-    a.truncated = truncated_dev + (long long)k0 * NA;
-    const int rc = launch(e, a, OP_STEP, (cudaStream_t)stream);
-    if (rc != PGM_OK) return rc;
-    k0 += k;
-  }
-  return PGM_OK;
+  a.rewards = rewards_dev;
+  a.terminated = terminated_dev;
+  a.truncated = truncated_dev;
+  return launch(e, a, OP_STEP, (cudaStream_t)stream);
 }
 int pgm_get_state(pgm_engine* e, int32_t what, void* dst, int64_t dst_bytes, void* stream) {
   if (!e || !dst) return fail(PGM_ERR_INVALID, "null argument");

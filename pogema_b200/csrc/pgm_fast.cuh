@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(1024, 1) pgm_fast_step_kernel(const StepArgs p
   }
 
   const int num_steps = p.num_steps;
-  int obs_slot = p.obs_slot0;
-  uint8_t* obs_cur = p.obs != nullptr ? p.obs + (long long)obs_slot * p.obs_slot_stride : nullptr;
+  int obs_slot = 0;
+  uint8_t* obs_cur = p.obs;
   // per-thread output cursors: agent q of this thread sits q * TEAM elements further (a compile-time offset)
   float* rew_ptr = p.rewards + (ia + tid);
   uint8_t* term_ptr = p.terminated + (ia + tid);

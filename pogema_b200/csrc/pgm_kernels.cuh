@@ -79,8 +79,7 @@ struct StepArgs {
   int num_steps;               // steps advanced by this launch (pgm_step_many)
   long long act_step_stride;   // bytes between the action tensors of consecutive steps
   long long out_step_stride;   // elements between rewards/terminated/truncated of consecutive steps
-  int obs_ring;                // step k writes observation slot (obs_slot0 + k) % obs_ring
-  int obs_slot0;               // (a long rollout is cut into several launches: the later ones start further on)
+  int obs_ring;                // step k writes observation slot k % obs_ring
   long long obs_slot_stride;   // bytes between observation slots
   uint8_t* obs;
   long long obs_inst_stride;  // bytes
@@ -660,7 +659,7 @@ __global__ void __launch_bounds__(1024, 1)
   // where every team runs its own timeline: no grid-wide barrier between steps, the observation
   // stores of one instance overlap the move phases of the others).
   const int num_steps = (OP == OP_STEP) ? p.num_steps : 1;
-  int obs_slot = p.obs_slot0;  // (obs_slot0 + k) % obs_ring without a division per step
+  int obs_slot = 0;  // k % obs_ring without a division per step
 #pragma unroll 1
   for (int k = 0; k < num_steps; ++k) {
     uint8_t* obs_k = p.obs;

@@ -379,7 +379,6 @@ StepArgs make_args(pgm_engine* e) {
   a.act_step_stride = 0;
   a.out_step_stride = 0;
   a.obs_ring = 1;
-  a.obs_slot0 = 0;
   a.obs_slot_stride = 0;
   a.obs = nullptr;
   a.obs_inst_stride = e->obs_inst_stride;

@@ -129,9 +129,9 @@ def test_fast_kernel_falls_back_on_misaligned_observation_pointers(monkeypatch):
 
 @pytest.mark.parametrize("fast", [True, False])
 @pytest.mark.parametrize("K,ring", [(40, 3), (25, 4), (33, 33), (64, 1)])
-def test_long_rollouts_are_cut_into_launches(fast, K, ring, monkeypatch):
-    """pgm_step_many with more than 24 steps goes out as launches of <= 16 steps: same results, every step's
-    observation in slot k % ring, outputs at [k]."""
+def test_long_rollouts(fast, K, ring, monkeypatch):
+    """pgm_step_many with many steps per launch and observation rings that do not divide K: same results as K single
+    steps, every step's observation in slot k % ring, outputs at [k]."""
     import torch
     gc = dict(size=14, density=0.2, num_agents=32, obs_radius=3, max_episode_steps=11, collision_system="soft",
               on_target="restart")
@@ -140,10 +140,8 @@ def test_long_rollouts_are_cut_into_launches(fast, K, ring, monkeypatch):
     b = build(gc, n, list(range(n)), monkeypatch, fast)
     a.reset(), b.reset()
     acts = torch.from_numpy(make_actions(K, n, 32, seed=K)).cuda()
-    launches0 = a.engine.launch_count
     obs_ring = torch.zeros((ring,) + tuple(a.engine.obs_shape()), dtype=torch.uint8, device="cuda")
     obs, rew, term, trunc = a.rollout(acts, obs_out=obs_ring)
-    assert a.engine.launch_count - launches0 == (K + 15) // 16
     last = {}
     for k in range(K):
         o, r, te, tr = b.step(acts[k])

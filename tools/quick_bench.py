@@ -19,6 +19,7 @@ ap.add_argument("--map", default="random", choices=["random", "maze", "warehouse
 ap.add_argument("--max-steps", type=int, default=64)
 ap.add_argument("--graph", type=int, default=0)
 ap.add_argument("--many", type=int, default=0, help="steps per launch (pgm_step_many)")
+ap.add_argument("--sets", type=int, default=0, help="with --many: rotate over this many sets of action / reward / flag tensors (the memory footprint of a longer rollout at the same steps per launch)")
 ap.add_argument("--ring", type=int, default=4, help="observation buffers written in turn (1: the same buffer every step - it may stay in L2)")
 a = ap.parse_args()
 from pogema_b200.maps import maze_map, warehouse_map
@@ -44,10 +45,23 @@ if a.many:
     torch.cuda.synchronize()
     reps = max(1, a.steps // K)
     a.steps = reps * K
-    e0.record()
-    for _ in range(reps):
-        env.rollout(act_k, obs_out=ring, compute_obs=not a.noobs)
-    e1.record()
+    if a.sets:
+        N, A = env.num_envs, env.num_agents
+        sets = [(act_k.clone(), torch.empty((K, N, A), dtype=torch.float32, device="cuda"),
+                 torch.empty((K, N, A), dtype=torch.bool, device="cuda"), torch.empty((K, N, A), dtype=torch.bool, device="cuda"))
+                for _ in range(a.sets)]
+        sp = int(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            ac, rw, te, tr = sets[i % a.sets]
+            env.engine.step_many(K, ac.data_ptr(), 1, ring.data_ptr(), a.ring, rw.data_ptr(), te.data_ptr(), tr.data_ptr(), sp)
+        e1.record()
+    else:
+        e0.record()
+        for _ in range(reps):
+            env.rollout(act_k, obs_out=ring, compute_obs=not a.noobs)
+        e1.record()
 elif a.graph:
     g = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
