@@ -848,9 +848,11 @@ __global__ void __launch_bounds__(1024, 1)
             p.rng[ia + a] = g;
           }
         }
-        p.rewards[oa + a] = rew;
-        p.terminated[oa + a] = term;
-        p.truncated[oa + a] = trunc ? 1 : 0;
+        // evict-first like the observations: written once, read by the caller - as ordinary lines the rewards and
+        // flags of a rollout pile up in L2 at the expense of the observation stream (pgm_fast.cuh has the numbers)
+        __stcs(p.rewards + oa + a, rew);
+        __stcs(p.terminated + oa + a, term);
+        __stcs(p.truncated + oa + a, (uint8_t)(trunc ? 1 : 0));
         p.was_on_goal[ia + a] = (uint8_t)was;
         uint32_t pp = s_npos[a];
         if (ONTGT == 1) solve_time_update(p.solve + 2 * (ia + a), was != 0u, pp != s_pos[a], s_pos[a] == tt, done, m_acc2);
