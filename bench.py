@@ -21,6 +21,8 @@ The same line carries, measured after the timed region:
     configs        the other BASELINE.json configurations (configs[2], [3], [4] r=3/5/7 at this world size),
                    both launch forms, each against its own algorithmic bytes
     e2e            pgm_step_host with HOST buffers (copies inside the timed windows)
+    roofline.lone_launch_behind_foreign_rollout   the K timed steps again, L2 flushed by a second engine's rollout
+                   instead of the ordinary 384 MB fill (whose lines stay in L2 and outrank the evict-first observations)
     sharding_check rank k's results == the C oracle / a single-GPU run of the same global seeds
     cpu_baseline   the oracle port on the host cores (N=1 only)
 
@@ -482,6 +484,37 @@ def run_cuda(args):
     r = WORKLOAD["obs_radius"]
     P = WORKLOAD["size"] + 2 * r
     bpa = algorithmic_bytes_per_agent_step(r, A, P)
+    # ---- what the lone K-step launch of the headline pays for (tools/lone_launch.py): the 384 MB fill in front of it
+    # leaves L2 full of ORDINARY dirty lines, which outrank the kernel's evict-first observation lines for the whole
+    # timed region.  The same launches behind a 16-step rollout of a second engine of the same shape (L2 flushed by
+    # 1.5 GB of foreign evict-first lines instead: cold for the timed launch, nothing squats):
+    lone = None
+    if SPL > 1 and not args.no_configs:
+        ef = BatchedPogema(gc, num_envs=N, device=dev, seeds=seeds + np.uint64(1 << 20), auto_reset=True)
+        ef.reset()
+        hf = Harness(torch, ef, dev, 777 + rank, SPL)
+        hf.alloc_outputs(16)
+        hf.many([16, 16])
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            hf.many([16])
+            e0.record(h.stream)
+            h.many(sizes)
+            e1.record(h.stream)
+            torch.cuda.synchronize()
+            ts.append(max_over_ranks(e0.elapsed_time(e1)))
+        ms_lone = sorted(ts)[len(ts) // 2] / args.steps
+        lone = {"us_per_step": ms_lone * 1e3, "frac": N * A * bpa / (ms_lone * 1e-3) / 1e9 / peak,
+                "how": "the same %d timed steps behind a 16-step rollout of a second engine (1.5 GB of evict-first stores to "
+                       "foreign buffers flush L2) instead of the 384 MB ordinary fill of the headline, whose lines stay in L2 "
+                       "and outrank the kernel's evict-first observation lines; median of 5" % args.steps}
+        ef.check_errors()
+        ef.close()
+        del hf, ef
+        torch.cuda.empty_cache()
     forms = measure_forms(h, N, A, bpa)
     closed_loop = None
     if "one_launch_per_step" in forms:
@@ -624,7 +657,8 @@ def run_cuda(args):
                              if plan_main.get("fast_step_kernel") else "pgm_step_kernel", SPL)),
                          "algorithmic_bytes_per_launch": N * A * bpa * (sizes[0] if sizes else 1),
                          "steady_state": {"frac": steady["roofline_frac"], "us_per_step": steady["us_per_step"], "steps": steady["steps"],
-                                          "note": "same kernel over a longer window (16 steps per launch), for comparison with the K-step headline"}},
+                                          "note": "same kernel over a longer window (16 steps per launch), for comparison with the K-step headline"},
+                         "lone_launch_behind_foreign_rollout": lone},
             "e2e": e2e,
             "e2e_other_transport": e2e_other,
             "gpu_launches": launches,
