@@ -40,7 +40,7 @@ def __getattr__(name):
         from . import envs
         return getattr(envs, name)
     if name in ("AnimationMonitor", "AnimationConfig", "PersistentWrapper", "AgentState", "AutoResetWrapper",
-                "SingleAgentWrapper", "IsMultiAgentWrapper", "MetricsForwardingWrapper", "RuntimeMetricWrapper"):
+                "SingleAgentWrapper", "IsMultiAgentWrapper", "MetricsForwardingWrapper", "RuntimeMetricWrapper", "AgentsDensityWrapper"):
         from . import wrappers
         return getattr(wrappers, name)
     if name == "parallel_env":

@@ -346,6 +346,45 @@ class RuntimeMetricWrapper(_Wrapper):
         return obs, rewards, terminated, truncated, infos
 
 
+class AgentsDensityWrapper(_Wrapper):
+    """upstream wrappers/metrics.py :: AgentsDensityWrapper (opt-in upstream too; for ``observation_type`` 'POMAPF' /
+    'MAPF'): ``metrics['avg_agents_density']`` = the episode's mean, reset observation included, of the per-step mean
+    over agents of (agents visible in the window / traversable cells of the window)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self._densities = []
+
+    def _count(self, observations):
+        if not isinstance(observations[0], dict):
+            raise TypeError("AgentsDensityWrapper needs dict observations (GridConfig(observation_type='POMAPF' or 'MAPF'))")
+        per_agent = [np.count_nonzero(o['agents']) / (np.size(o['obstacles']) - np.count_nonzero(o['obstacles']))
+                     for o in observations]
+        self._densities.append(np.mean(per_agent))
+
+    def reset(self, **kwargs):
+        self._densities = []
+        observations, infos = self.env.reset(**kwargs)
+        self._count(observations)
+        return observations, infos
+
+    def step(self, action):
+        observations, rewards, terminated, truncated, infos = self.env.step(action)
+        if all(terminated) or all(truncated):
+            # (with GridConfig(auto_reset=True) `observations` is already the next episode's reset observation: it
+            # opens the next episode's mean instead of closing this one's)
+            auto = bool(getattr(self.env.unwrapped.grid_config, 'auto_reset', None))
+            if not auto:
+                self._count(observations)
+            infos[0].setdefault('metrics', {})['avg_agents_density'] = float(np.mean(self._densities))
+            if auto:
+                self._densities = []
+                self._count(observations)
+        else:
+            self._count(observations)
+        return observations, rewards, terminated, truncated, infos
+
+
 class AutoResetWrapper(_Wrapper):
     """upstream integrations/sample_factory.py :: AutoResetWrapper: when every agent is terminated or truncated the
     env is reset inside ``step`` and the returned observation is the reset one (``GridConfig(auto_reset=True)``

@@ -90,3 +90,23 @@ def test_list_api_reports_soc_makespan_and_runtime():
     assert out[3] == [True] * 3
     assert out[4][0]["metrics"] == rout[4][0]["metrics"]
     assert out[4][0]["metrics"]["SoC"] == (2 + 0 + 4) + 3 and out[4][0]["metrics"]["makespan"] == 5
+
+
+@pytest.mark.parametrize("kind", ["POMAPF", "MAPF"])
+def test_agents_density_wrapper_matches_the_oracle(kind):
+    from pogema_b200 import AgentsDensityWrapper, GridConfig, pogema_v0
+    kw = dict(size=8, density=0.2, num_agents=6, obs_radius=2, max_episode_steps=7, seed=3, observation_type=kind)
+    env = AgentsDensityWrapper(pogema_v0(GridConfig(**kw)))
+    ref = orc.AgentsDensityWrapper(orc.pogema_v0(orc.GridConfig(**kw)))
+    env.reset(), ref.reset()
+    rng = np.random.default_rng(0)
+    seen = 0
+    for t in range(24):
+        acts = [int(v) for v in rng.integers(0, 5, size=6)]
+        out, rout = env.step(acts), ref.step(acts)
+        assert out[4][0].get("metrics") == rout[4][0].get("metrics"), t
+        if "metrics" in out[4][0]:
+            assert "avg_agents_density" in out[4][0]["metrics"]
+            seen += 1
+            env.reset(), ref.reset()
+    assert seen >= 3

@@ -107,3 +107,29 @@ def test_lifelong_new_target_comes_from_the_agents_generator():
     _, rew, term, _, _ = env.step([4])
     assert rew == [1.0] and term == [False]
     assert env.unwrapped.grid.finishes_xy[0] == exp
+
+
+def test_density_and_runtime_wrappers_of_the_package_on_the_oracle_env():
+    """pogema_b200's host-side metric wrappers are plain Python over the env API: wrapped around the ORACLE env they must
+    report what the oracle's own restatement of upstream's wrappers reports (no GPU, no engine involved)."""
+    from pogema_b200.wrappers import AgentsDensityWrapper, RuntimeMetricWrapper
+    kw = dict(size=8, density=0.2, num_agents=6, obs_radius=2, max_episode_steps=7, seed=3, observation_type="POMAPF")
+    a = RuntimeMetricWrapper(AgentsDensityWrapper(orc.pogema_v0(orc.GridConfig(**kw))))
+    b = orc.RuntimeMetricWrapper(orc.AgentsDensityWrapper(orc.pogema_v0(orc.GridConfig(**kw))))
+    a.reset(), b.reset()
+    rng = np.random.default_rng(0)
+    seen = 0
+    for t in range(30):
+        acts = [int(v) for v in rng.integers(0, 5, size=6)]
+        ra, rb = a.step(acts), b.step(acts)
+        ma, mb = ra[4][0].get("metrics"), rb[4][0].get("metrics")
+        assert (ma is None) == (mb is None)
+        if ma is not None:
+            ma, mb = dict(ma), dict(mb)
+            assert 0.0 <= ma.pop("runtime") < 5.0 and 0.0 <= mb.pop("runtime") < 5.0
+            assert ma == mb and 0.0 < ma["avg_agents_density"] <= 1.0
+            seen += 1
+            a.reset(), b.reset()
+    assert seen >= 3
+    with pytest.raises(TypeError):
+        AgentsDensityWrapper(orc.pogema_v0(orc.GridConfig(size=8, num_agents=2, seed=0))).reset()
