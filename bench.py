@@ -210,11 +210,12 @@ def measured_peak_gbs():
 
 
 def ncu_traffic_bytes():
-    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+    """(dram bytes per launch, steps of that launch, source) of the step kernel from the committed ncu capture, if any."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get("dram_bytes_per_launch")
+            t = json.load(open(path))
+            return t.get("dram_bytes_per_launch"), int(t.get("steps_per_launch", 1)), t.get("source")
         except Exception:
             return None
     return None
@@ -637,7 +638,10 @@ def run_cuda(args):
     sharding = sharding_check(torch, dist, np, BatchedPogema, gc, dev, rank, world, N, A)
 
     if rank == 0:
-        traffic = ncu_traffic_bytes()
+        # dram bytes of ONE launch as timed here: the ncu capture is a 16-step launch, scaled to this launch's steps
+        cap = ncu_traffic_bytes()
+        steps_in_launch = sizes[0] if sizes else 1
+        traffic = cap[0] / cap[1] * steps_in_launch if cap and cap[0] else None
         achieved = N * A * bpa / (ms_per_step * 1e-3) / 1e9
         cfg = workload_config(world, N)
         line = {
@@ -651,7 +655,10 @@ def run_cuda(args):
                         else (("one launch per step, CUDA graph of %d launches replayed" % h.graph_steps) if h.graph is not None else "one pgm_step call per step"),
                         "steps_per_launch": SPL, "plan": plan_main},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000_GBps": achieved / 8000.0,
+                         "traffic": traffic,
+                         "traffic_source": ("%s: %.1f MB per %d-step launch = %.1f MB per step, x %d steps of the timed launch"
+                                            % (cap[2], cap[0] / 1e6, cap[1], cap[0] / cap[1] / 1e6, steps_in_launch)) if traffic else None,
+                         "peak_source": peak_src, "frac_of_nominal_8000_GBps": achieved / 8000.0,
                          "algorithmic_bytes_per_agent_step": bpa, "kernel": ("%s (pgm_step_many, up to %d steps per launch)" % (
                              ("pgm_fast_step_kernel<%d,%d,...>" % (plan_main["fast"]["team_threads"], plan_main["fast"]["agents_per_thread"]))
                              if plan_main.get("fast_step_kernel") else "pgm_step_kernel", SPL)),
