@@ -22,7 +22,7 @@ The same line carries, measured after the timed region:
                    both launch forms, each against its own algorithmic bytes
     e2e            pgm_step_host with HOST buffers (copies inside the timed windows)
     roofline.lone_launch_behind_foreign_rollout   the K timed steps again, L2 flushed by a second engine's rollout
-                   instead of the ordinary 384 MB fill (whose lines stay in L2 and outrank the evict-first observations)
+                   instead of the ordinary 1 GB fill (whose lines stay in L2 and outrank the evict-first observations)
     sharding_check rank k's results == the C oracle / a single-GPU run of the same global seeds
     cpu_baseline   the oracle port on the host cores (N=1 only)
 
@@ -317,12 +317,14 @@ class Harness:
         self.graph, self.graph_steps = g, steps
 
     def timed(self, fn):
-        """CUDA-event time of the launches fn() enqueues.  A 384 MB fill runs right before the first event: it
+        """CUDA-event time of the launches fn() enqueues.  A 1 GB fill runs right before the first event: it
         flushes L2 (126 MB) and keeps the GPU busy while the CPU enqueues the timed launches, so the events
-        bracket device time only (the kernels are queued by the time the fill ends), not ctypes / launch latency."""
+        bracket device time only (the kernels are queued by the time the fill ends), not ctypes / launch latency.  (1 GB
+        = ~0.3 ms of cover: with 384 MB = ~0.12 ms one box of the pool timed the 20-step launch at 16.8 instead of
+        16.3 us per step although its steady-state and behind-a-rollout figures were the usual ones - its host was late.)"""
         torch = self.torch
         if not hasattr(self, "flush"):
-            self.flush = torch.empty(384 << 20, dtype=torch.uint8, device=self.dev)
+            self.flush = torch.empty(1024 << 20, dtype=torch.uint8, device=self.dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.flush.fill_(1)
         e0.record(self.stream)
@@ -485,7 +487,7 @@ def run_cuda(args):
     r = WORKLOAD["obs_radius"]
     P = WORKLOAD["size"] + 2 * r
     bpa = algorithmic_bytes_per_agent_step(r, A, P)
-    # ---- what the lone K-step launch of the headline pays for (tools/lone_launch.py): the 384 MB fill in front of it
+    # ---- what the lone K-step launch of the headline pays for (tools/lone_launch.py): the 1 GB fill in front of it
     # leaves L2 full of ORDINARY dirty lines, which outrank the kernel's evict-first observation lines for the whole
     # timed region.  The same launches behind a 16-step rollout of a second engine of the same shape (L2 flushed by
     # 1.5 GB of foreign evict-first lines instead: cold for the timed launch, nothing squats):
@@ -510,7 +512,7 @@ def run_cuda(args):
         ms_lone = sorted(ts)[len(ts) // 2] / args.steps
         lone = {"us_per_step": ms_lone * 1e3, "frac": N * A * bpa / (ms_lone * 1e-3) / 1e9 / peak,
                 "how": "the same %d timed steps behind a 16-step rollout of a second engine (1.5 GB of evict-first stores to "
-                       "foreign buffers flush L2) instead of the 384 MB ordinary fill of the headline, whose lines stay in L2 "
+                       "foreign buffers flush L2) instead of the 1 GB ordinary fill of the headline, whose lines stay in L2 "
                        "and outrank the kernel's evict-first observation lines; median of 5" % args.steps}
         ef.check_errors()
         ef.close()

@@ -1,5 +1,5 @@
 """What does the lone K-step launch of the driver's invocation (bench.py --steps 20) pay for?  The same launch timed
- (a) behind the 384 MB torch fill bench.py uses (L2 ends up full of ORDINARY dirty lines, which outrank the kernel's
+ (a) behind a 384 MB torch fill (bench.py uses 1 GB: same L2 state, longer cover) (L2 ends up full of ORDINARY dirty lines, which outrank the kernel's
      evict-first observation lines for the whole timed region),
  (b) behind a 16-step rollout of a second engine of the same shape into its own buffers (L2 full of evict-first lines of
      foreign buffers: cold for the timed launch, but nothing squats), and
