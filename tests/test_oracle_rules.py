@@ -133,3 +133,18 @@ def test_density_and_runtime_wrappers_of_the_package_on_the_oracle_env():
     assert seen >= 3
     with pytest.raises(TypeError):
         AgentsDensityWrapper(orc.pogema_v0(orc.GridConfig(size=8, num_agents=2, seed=0))).reset()
+
+
+def test_two_recollections_of_the_soft_rule_agree():
+    """SURVEY.md section 9 item 1 (LOW confidence upstream): a second, independently recalled form of `soft` /
+    `_revert_action` (tools/prototypes/soft_variants.py: obstacle test folded into the vertex pass, only the first
+    follower reverted per recursion, stays taking part in the swap test) gives the oracle's result on random crowded
+    scenarios (93 000 scenarios when run as a script)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "prototypes", "soft_variants.py")
+    spec = importlib.util.spec_from_file_location("soft_variants", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    moved, cancelled = mod.fuzz(600, seed=11)
+    assert moved > 2000 and cancelled > 2000
